@@ -1,0 +1,219 @@
+"""ctypes binding of libgsn.so (include/gsn.h) -- the only way Python reaches the GPU.
+
+There is no CPU implementation behind these calls: if the library is missing, or
+no CUDA device is present, they raise.  PyTorch is used by callers for device
+memory and streams only; nothing here imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import build as _build
+
+# --- enums (values fixed by include/gsn.h) ---------------------------------
+K_EXPSQUARED, K_EXPONENTIAL, K_CONSTANT, K_DOTPRODUCT, K_MATERN32, K_MATERN52, K_RATQUAD, K_GIBBS, K_OU, K_PERIODIC, K_JJ = range(11)
+M_UNIFORM, M_SIN, M_GAUSSIAN, M_EXPFUNCTION, M_BAZIN2009, M_KARPENKA2012, M_VILLAR2019, M_HOST = range(8)
+L_NONE, L_CONSTANT, L_SIGMOID, L_SINUSOIDAL = range(4)
+FLAG_NEG_INF = 1
+Q_N, Q_NPARAMS, Q_NPARAMS_KERNEL, Q_NPARAMS_MEAN, Q_NPARAMS_LENS, Q_WORKSPACE_BYTES, Q_GRID, Q_DEVICE, Q_LAUNCHES, Q_NPAD, Q_PATH = range(11)
+ABI_VERSION = 1
+
+EXPORTED_SYMBOLS = (
+    "gsn_problem_create", "gsn_problem_destroy", "gsn_problem_set_theta_map", "gsn_logl_batch",
+    "gsn_logl_batch_host", "gsn_logl_batch_hostmean", "gsn_lens_batch", "gsn_query", "gsn_covariance",
+    "gsn_mean", "gsn_lens", "gsn_kernel_nparams", "gsn_mean_nparams", "gsn_lens_nparams",
+    "gsn_abi_version", "gsn_last_error",
+)
+
+
+class GsnError(RuntimeError):
+    """A libgsn call returned a negative status."""
+
+
+_lib = None
+_lib_lock = threading.Lock()
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load libgsn.so (never builds implicitly unless GSN_AUTOBUILD=1)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = lib_path()
+        if not os.path.exists(path):
+            if os.environ.get("GSN_AUTOBUILD") == "1":
+                _build.build_lib()
+            else:
+                raise GsnError(
+                    f"{path} not found: build the CUDA library first "
+                    "(python -c 'import __graft_entry__ as g; g.build()' or python -m gaussn_b200.build). "
+                    "gaussn_b200 has no CPU fallback.")
+        lib = C.CDLL(path)
+        lib.gsn_abi_version.restype = C.c_int32
+        if lib.gsn_abi_version() != ABI_VERSION:
+            raise GsnError(f"libgsn ABI {lib.gsn_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+        lib.gsn_last_error.restype = C.c_char_p
+        lib.gsn_problem_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int64, _dp, _dp, _dp, C.c_int32, C.c_int32,
+                                           _lp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+        lib.gsn_problem_destroy.argtypes = [C.c_void_p]
+        lib.gsn_problem_set_theta_map.argtypes = [C.c_void_p, _ip, _dp]
+        lib.gsn_logl_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.gsn_logl_batch_host.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_uint32]
+        lib.gsn_logl_batch_hostmean.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.gsn_lens_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gsn_query.argtypes = [C.c_void_p, C.c_int32]
+        lib.gsn_query.restype = C.c_int64
+        lib.gsn_covariance.argtypes = [C.c_int, C.c_int32, _dp, C.c_int32, _dp, C.c_int64, _dp, C.c_int64, _dp]
+        lib.gsn_mean.argtypes = [C.c_int, C.c_int32, _dp, C.c_int32, _dp, C.c_int64, _dp]
+        lib.gsn_lens.argtypes = [C.c_int, C.c_int32, _dp, C.c_int32, _dp, C.c_int64, C.c_int32, C.c_int32, _lp, _dp, _dp]
+        for name in ("gsn_kernel_nparams", "gsn_mean_nparams"):
+            getattr(lib, name).argtypes = [C.c_int32]
+            getattr(lib, name).restype = C.c_int32
+        lib.gsn_lens_nparams.argtypes = [C.c_int32, C.c_int32]
+        lib.gsn_lens_nparams.restype = C.c_int32
+        _lib = lib
+        return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise GsnError(f"libgsn error {rc}: {load().gsn_last_error().decode()}")
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_dp)
+
+
+def default_device() -> int:
+    return int(os.environ.get("LOCAL_RANK", os.environ.get("GSN_DEVICE", "0")))
+
+
+# --- single-call plugin evaluations ----------------------------------------
+def covariance(kind: int, params, x, x_prime=None, device=None) -> np.ndarray:
+    lib = load()
+    x = _f64(x).ravel()
+    xp = None if x_prime is None else _f64(x_prime).ravel()
+    p = _f64(params if params is not None else []).ravel()
+    n, m = len(x), (len(x) if xp is None else len(xp))
+    out = np.empty((n, m), dtype=np.float64)
+    _check(lib.gsn_covariance(default_device() if device is None else device, kind, _ptr(p) if len(p) else None, len(p),
+                              _ptr(x), n, None if xp is None else _ptr(xp), m, _ptr(out)))
+    return out
+
+
+def mean(kind: int, params, t, device=None) -> np.ndarray:
+    lib = load()
+    t = _f64(t).ravel()
+    p = _f64(params).ravel()
+    out = np.empty(len(t), dtype=np.float64)
+    _check(lib.gsn_mean(default_device() if device is None else device, kind, _ptr(p), len(p), _ptr(t), len(t), _ptr(out)))
+    return out
+
+
+def lens(kind: int, params, x, n_bands: int, n_images: int, indices, device=None):
+    lib = load()
+    x = _f64(x).ravel()
+    p = _f64(params if params is not None else []).ravel()
+    idx = np.ascontiguousarray(np.asarray(indices, dtype=np.int64))
+    xs = np.empty(len(x), dtype=np.float64)
+    b = np.empty(len(x), dtype=np.float64)
+    _check(lib.gsn_lens(default_device() if device is None else device, kind, _ptr(p) if len(p) else None, len(p), _ptr(x),
+                        len(x), n_bands, n_images, idx.ctypes.data_as(_lp), _ptr(xs), _ptr(b)))
+    return xs, b
+
+
+# --- problem handle ---------------------------------------------------------
+class Problem:
+    """Owns one ``gsn_problem``: a data set plus a plugin triple on one GPU."""
+
+    def __init__(self, x, y, yerr, n_bands, n_images, indices, kernel_kind, mean_kind, lens_kind,
+                 n_mean_params=-1, device=None):
+        self._lib = load()
+        self._h = C.c_void_p()
+        self.device = default_device() if device is None else int(device)
+        x, y, yerr = _f64(x).ravel(), _f64(y).ravel(), _f64(yerr).ravel()
+        if not (len(x) == len(y) == len(yerr)):
+            raise ValueError("x, y and yerr must have the same length")
+        idx = np.ascontiguousarray(np.asarray(indices, dtype=np.int64))
+        if len(idx) != n_bands * n_images + 1:
+            raise ValueError("indices must have n_bands*n_images + 1 entries")
+        _check(self._lib.gsn_problem_create(C.byref(self._h), self.device, len(x), _ptr(x), _ptr(y), _ptr(yerr), n_bands,
+                                            n_images, idx.ctypes.data_as(_lp), kernel_kind, mean_kind, lens_kind, n_mean_params))
+        self.N = len(x)
+        self.n_params = int(self.query(Q_NPARAMS))
+        self.n_kernel = int(self.query(Q_NPARAMS_KERNEL))
+        self.n_mean = int(self.query(Q_NPARAMS_MEAN))
+        self.n_lens = int(self.query(Q_NPARAMS_LENS))
+        self.n_cols = self.n_params
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.gsn_problem_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def query(self, what: int) -> int:
+        return int(self._lib.gsn_query(self._h, what))
+
+    def set_theta_map(self, col_of_param=None, fixed_values=None):
+        """``col_of_param[k]`` = column of the caller's theta feeding slot k, or -1
+        (slot held at ``fixed_values[k]``).  ``None`` restores the identity map."""
+        if col_of_param is None:
+            _check(self._lib.gsn_problem_set_theta_map(self._h, None, None))
+            self.n_cols = self.n_params
+            return
+        cols = np.ascontiguousarray(np.asarray(col_of_param, dtype=np.int32))
+        fixed = _f64(np.zeros(self.n_params) if fixed_values is None else fixed_values)
+        if len(cols) != self.n_params or len(fixed) != self.n_params:
+            raise ValueError(f"theta map needs {self.n_params} entries")
+        _check(self._lib.gsn_problem_set_theta_map(self._h, cols.ctypes.data_as(_ip), _ptr(fixed)))
+        self.n_cols = int(cols.max()) + 1 if len(cols) else 0
+
+    # host buffers in, host buffers out (H2D / D2H inside the call)
+    def logl_host(self, theta, flags: int = 0, return_info: bool = False):
+        theta = _f64(theta)
+        if theta.ndim == 1:
+            theta = theta.reshape(1, -1)
+        B, ld = theta.shape
+        out = np.empty(B, dtype=np.float64)
+        info = np.empty(B, dtype=np.int32)
+        _check(self._lib.gsn_logl_batch_host(self._h, _ptr(theta) if theta.size else None, B, ld, _ptr(out),
+                                             info.ctypes.data_as(_ip), flags))
+        return (out, info) if return_info else out
+
+    # device pointers (torch tensors' data_ptr()), asynchronous on `stream`
+    def logl_device(self, theta_ptr: int, B: int, ld: int, logl_ptr: int, info_ptr: int = 0, flags: int = 0, stream: int = 0):
+        _check(self._lib.gsn_logl_batch(self._h, C.c_void_p(theta_ptr), B, ld, C.c_void_p(logl_ptr),
+                                        C.c_void_p(info_ptr) if info_ptr else None, flags, C.c_void_p(stream) if stream else None))
+
+    def logl_device_hostmean(self, theta_ptr: int, B: int, ld: int, mean_ptr: int, logl_ptr: int, info_ptr: int = 0,
+                             flags: int = 0, stream: int = 0):
+        _check(self._lib.gsn_logl_batch_hostmean(self._h, C.c_void_p(theta_ptr), B, ld, C.c_void_p(mean_ptr), C.c_void_p(logl_ptr),
+                                                 C.c_void_p(info_ptr) if info_ptr else None, flags,
+                                                 C.c_void_p(stream) if stream else None))
+
+    def lens_device(self, theta_ptr: int, B: int, ld: int, shifted_ptr: int, b_ptr: int, stream: int = 0):
+        _check(self._lib.gsn_lens_batch(self._h, C.c_void_p(theta_ptr), B, ld, C.c_void_p(shifted_ptr), C.c_void_p(b_ptr),
+                                        C.c_void_p(stream) if stream else None))

@@ -1,0 +1,505 @@
+// C ABI of libgsn.so (see include/gsn.h).  Host side: handle management, input
+// validation, workspace sizing, kernel dispatch.  No CPU compute path exists
+// here: every compute entry point launches CUDA kernels or fails.
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <new>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+
+#include "../../include/gsn.h"
+#include "gsn_device.cuh"
+#include "gsn_chol_dmma.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define GSN_CUDA(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t e_ = (expr);                                                                      \
+    if (e_ != cudaSuccess) return fail(GSN_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+    ok = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+struct gsn_problem {
+  int device = 0;
+  int sm_count = 0;
+  gsn::ProblemDev pd{};
+  int kernel_kind = 0;
+  // device buffers
+  double* d_x = nullptr; double* d_y = nullptr; double* d_yerr2 = nullptr;
+  int* d_img = nullptr; int* d_band = nullptr;
+  int* d_theta_col = nullptr; double* d_theta_fixed = nullptr;
+  double* d_workspace = nullptr; size_t slot_doubles = 0; size_t workspace_bytes = 0;
+  unsigned* d_counter = nullptr;
+  int grid = 0; size_t smem_bytes = 0;
+  int n_theta_cols = 0;   // columns the caller's theta must provide
+  // host staging for gsn_logl_batch_host
+  double* h_theta = nullptr; double* h_logl = nullptr; int* h_info = nullptr;
+  double* d_theta = nullptr; double* d_logl = nullptr; int* d_info = nullptr;
+  int64_t stage_rows = 0; int64_t stage_ld = 0;
+  cudaStream_t own_stream = nullptr;
+  long long launches = 0;
+};
+
+namespace {
+
+template <int KIND>
+int launch_logl(gsn_problem* p, const double* theta, int64_t B, int64_t ld, const double* hostmean,
+                double* logl, int* info, unsigned flags, cudaStream_t stream) {
+  static bool attr_set[64] = {};
+  auto kern = gsn::logl_dmma_kernel<KIND>;
+  if (!attr_set[p->device & 63]) {
+    GSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set[p->device & 63] = true;
+  }
+  GSN_CUDA(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned), stream));
+  const int grid = (int)std::min<int64_t>(B, p->grid);
+  kern<<<grid, gsn::kThreads, p->smem_bytes, stream>>>(p->pd, theta, B, ld, hostmean, logl, info, flags,
+                                                      p->d_workspace, p->slot_doubles, p->d_counter);
+  GSN_CUDA(cudaGetLastError());
+  p->launches += 1;
+  return GSN_OK;
+}
+
+int dispatch_logl(gsn_problem* p, const double* theta, int64_t B, int64_t ld, const double* hostmean,
+                  double* logl, int* info, unsigned flags, cudaStream_t stream) {
+  switch (p->kernel_kind) {
+#define GSN_CASE(K) case K: return launch_logl<K>(p, theta, B, ld, hostmean, logl, info, flags, stream)
+    GSN_CASE(GSN_K_EXPSQUARED);
+    GSN_CASE(GSN_K_EXPONENTIAL);
+    GSN_CASE(GSN_K_CONSTANT);
+    GSN_CASE(GSN_K_DOTPRODUCT);
+    GSN_CASE(GSN_K_MATERN32);
+    GSN_CASE(GSN_K_MATERN52);
+    GSN_CASE(GSN_K_RATQUAD);
+    GSN_CASE(GSN_K_GIBBS);
+    GSN_CASE(GSN_K_OU);
+    GSN_CASE(GSN_K_PERIODIC);
+    GSN_CASE(GSN_K_JJ);
+#undef GSN_CASE
+  }
+  return fail(GSN_ERR_INVALID, "unknown kernel kind %d", p->kernel_kind);
+}
+
+template <int KIND>
+__global__ void covariance_kernel(const double* __restrict__ kp, const double* __restrict__ x, long long n,
+                                  const double* __restrict__ xp, long long m, double* __restrict__ K) {
+  const gsn::KernelConsts kc = gsn::kernel_consts<KIND>(kp);
+  const long long total = n * m;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / m, j = idx % m;
+    const double xi = x[i], xj = xp[j];
+    // JJ: the period is _p(x)[j], i.e. taken from the FIRST argument at the column index (kernels.py:555)
+    const double ai = gsn::kernel_has_aux<KIND>() ? gsn::kernel_aux<KIND>(kc, xi) : 0.0;
+    const double aj = gsn::kernel_has_aux<KIND>() ? gsn::kernel_aux<KIND>(kc, KIND == GSN_K_JJ ? x[j] : xj) : 0.0;
+    K[idx] = gsn::cov_elem<KIND>(kc, xi, xj, ai, aj);
+  }
+}
+
+__global__ void mean_kernel(int kind, const double* __restrict__ mp, const double* __restrict__ t, long long n,
+                            double* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = gsn::mean_eval(kind, mp, t[i]);
+}
+
+__global__ void lens_kernel(int kind, const double* __restrict__ lp, const int* __restrict__ img,
+                            const double* __restrict__ x, long long n, double* __restrict__ xs, double* __restrict__ b) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double s, bb;
+    gsn::lens_eval(kind, lp, img[i], x[i], s, bb);
+    xs[i] = s; b[i] = bb;
+  }
+}
+
+int check_indices(const int64_t* indices, int32_t n_bands, int32_t n_images, int64_t N) {
+  if (!indices) return fail(GSN_ERR_INVALID, "indices is null");
+  const int64_t S = (int64_t)n_bands * n_images;
+  if (indices[0] != 0) return fail(GSN_ERR_INVALID, "indices[0] must be 0");
+  for (int64_t s = 0; s < S; ++s)
+    if (indices[s + 1] < indices[s]) return fail(GSN_ERR_INVALID, "indices must be non-decreasing");
+  if (indices[S] != N) return fail(GSN_ERR_INVALID, "indices[last] = %lld does not equal N = %lld", (long long)indices[S], (long long)N);
+  return GSN_OK;
+}
+
+// scratch RAII for the single-call helpers
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int32_t gsn_abi_version(void) { return GSN_ABI_VERSION; }
+const char* gsn_last_error(void) { return g_last_error.c_str(); }
+int32_t gsn_kernel_nparams(int32_t kind) { return gsn::kernel_nparams(kind); }
+int32_t gsn_mean_nparams(int32_t kind) { return gsn::mean_nparams(kind); }
+int32_t gsn_lens_nparams(int32_t kind, int32_t n_images) {
+  const int per = gsn::lens_nparams_per_image(kind);
+  if (per < 0 || n_images < 1) return -1;
+  return per * (n_images - 1);
+}
+
+int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x, const double* y, const double* yerr,
+                       int32_t n_bands, int32_t n_images, const int64_t* indices, int32_t kernel_kind,
+                       int32_t mean_kind, int32_t lens_kind, int32_t n_mean_params) {
+  if (!out) return fail(GSN_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (N < 1 || N > (1 << 20)) return fail(GSN_ERR_INVALID, "N = %lld out of range", (long long)N);
+  if (!x || !y || !yerr) return fail(GSN_ERR_INVALID, "x, y and yerr must be non-null");
+  if (n_bands < 1 || n_images < 1) return fail(GSN_ERR_INVALID, "n_bands and n_images must be >= 1");
+  if (n_images > gsn::kMaxImages) return fail(GSN_ERR_UNSUPPORTED, "at most %d images are supported", gsn::kMaxImages);
+  if (gsn::kernel_nparams(kernel_kind) < 0) return fail(GSN_ERR_INVALID, "unknown kernel kind %d", kernel_kind);
+  if (gsn::mean_nparams(mean_kind) < 0) return fail(GSN_ERR_INVALID, "unknown mean kind %d", mean_kind);
+  if (gsn::lens_nparams_per_image(lens_kind) < 0) return fail(GSN_ERR_INVALID, "unknown lensing kind %d", lens_kind);
+  if (int rc = check_indices(indices, n_bands, n_images, N)) return rc;
+  int nm = n_mean_params < 0 ? gsn::mean_nparams(mean_kind) : n_mean_params;
+  if (mean_kind != GSN_M_HOST && nm < gsn::mean_nparams(mean_kind))
+    return fail(GSN_ERR_INVALID, "mean kind %d needs %d parameters, got %d", mean_kind, gsn::mean_nparams(mean_kind), nm);
+  if (nm > gsn::kMaxMeanParams) return fail(GSN_ERR_UNSUPPORTED, "at most %d mean parameters", gsn::kMaxMeanParams);
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(GSN_ERR_CUDA, "no CUDA device available; libgsn has no CPU path");
+  if (device < 0 || device >= ndev) return fail(GSN_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(GSN_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  cudaDeviceProp prop;
+  GSN_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(GSN_ERR_UNSUPPORTED, "device %d is sm_%d%d; libgsn is built for sm_100a only", device, prop.major, prop.minor);
+
+  gsn_problem* p = new (std::nothrow) gsn_problem();
+  if (!p) return fail(GSN_ERR_INVALID, "out of host memory");
+  p->device = device;
+  p->sm_count = prop.multiProcessorCount;
+  p->kernel_kind = kernel_kind;
+  gsn::ProblemDev& pd = p->pd;
+  pd.N = (int)N;
+  pd.Npad = (int)((N + 31) / 32 * 32);
+  pd.nblk = pd.Npad / 32;
+  pd.n_images = n_images;
+  pd.mean_kind = mean_kind;
+  pd.lens_kind = lens_kind;
+  pd.use_mask = (lens_kind != GSN_L_NONE) ? 1 : 0;  // NoLensing.mask = 1 (lensingmodels.py:10)
+  pd.nk = gsn::kernel_nparams(kernel_kind);
+  pd.nm = nm;
+  pd.nl = gsn::lens_nparams_per_image(lens_kind) * (n_images - 1);
+  pd.P = pd.nk + pd.nm + pd.nl;
+  pd.nlog2pi = (double)N * std::log(2.0 * M_PI);
+  p->n_theta_cols = pd.P;
+
+  // per-epoch tables (padded)
+  std::vector<double> hx(pd.Npad, 0.0), hy(pd.Npad, 0.0), he(pd.Npad, 1.0);
+  std::vector<int> himg(pd.Npad, 0), hband(pd.Npad, -1);
+  for (int64_t i = 0; i < N; ++i) { hx[i] = x[i]; hy[i] = y[i]; he[i] = yerr[i] * yerr[i]; }
+  for (int b = 0; b < n_bands; ++b)
+    for (int im = 0; im < n_images; ++im) {
+      const int s = b * n_images + im;   // band-major, image-minor: gausSN.py:83-91, lensingmodels.py:94
+      for (int64_t i = indices[s]; i < indices[s + 1]; ++i) { himg[i] = im; hband[i] = b; }
+    }
+  std::vector<int> hcol(std::max(pd.P, 1));
+  std::vector<double> hfix(std::max(pd.P, 1), 0.0);
+  for (int k = 0; k < pd.P; ++k) hcol[k] = k;
+
+  auto cleanup = [&](int rc) { gsn_problem_destroy(p); return rc; };
+#define GSN_CUDA_P(expr)                                                                                       \
+  do {                                                                                                         \
+    cudaError_t e_ = (expr);                                                                                   \
+    if (e_ != cudaSuccess) return cleanup(fail(GSN_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_))); \
+  } while (0)
+  const size_t nb = sizeof(double) * pd.Npad;
+  GSN_CUDA_P(cudaMalloc(&p->d_x, nb));
+  GSN_CUDA_P(cudaMalloc(&p->d_y, nb));
+  GSN_CUDA_P(cudaMalloc(&p->d_yerr2, nb));
+  GSN_CUDA_P(cudaMalloc(&p->d_img, sizeof(int) * pd.Npad));
+  GSN_CUDA_P(cudaMalloc(&p->d_band, sizeof(int) * pd.Npad));
+  GSN_CUDA_P(cudaMalloc(&p->d_theta_col, sizeof(int) * hcol.size()));
+  GSN_CUDA_P(cudaMalloc(&p->d_theta_fixed, sizeof(double) * hfix.size()));
+  GSN_CUDA_P(cudaMalloc(&p->d_counter, sizeof(unsigned)));
+  GSN_CUDA_P(cudaMemcpy(p->d_x, hx.data(), nb, cudaMemcpyHostToDevice));
+  GSN_CUDA_P(cudaMemcpy(p->d_y, hy.data(), nb, cudaMemcpyHostToDevice));
+  GSN_CUDA_P(cudaMemcpy(p->d_yerr2, he.data(), nb, cudaMemcpyHostToDevice));
+  GSN_CUDA_P(cudaMemcpy(p->d_img, himg.data(), sizeof(int) * pd.Npad, cudaMemcpyHostToDevice));
+  GSN_CUDA_P(cudaMemcpy(p->d_band, hband.data(), sizeof(int) * pd.Npad, cudaMemcpyHostToDevice));
+  GSN_CUDA_P(cudaMemcpy(p->d_theta_col, hcol.data(), sizeof(int) * hcol.size(), cudaMemcpyHostToDevice));
+  GSN_CUDA_P(cudaMemcpy(p->d_theta_fixed, hfix.data(), sizeof(double) * hfix.size(), cudaMemcpyHostToDevice));
+  pd.x = p->d_x; pd.y = p->d_y; pd.yerr2 = p->d_yerr2; pd.img = p->d_img; pd.band = p->d_band;
+  pd.theta_col = p->d_theta_col; pd.theta_fixed = p->d_theta_fixed;
+
+  // persistent grid: CTAs/SM limited by registers (launch bounds) and shared memory
+  p->smem_bytes = gsn::logl_dmma_smem_bytes(pd.Npad);
+  if (p->smem_bytes > 200 * 1024) return cleanup(fail(GSN_ERR_UNSUPPORTED, "N = %lld needs %zu bytes of shared memory", (long long)N, p->smem_bytes));
+  int per_sm = (int)std::min<size_t>(gsn::kMinCtasPerSm, (size_t)(227 * 1024) / (p->smem_bytes + 1024));
+  per_sm = std::max(per_sm, 1);
+  p->slot_doubles = gsn::logl_dmma_slot_doubles(pd.Npad);
+  // bound the workspace to a quarter of device memory for very large N
+  size_t free_b = 0, total_b = 0;
+  GSN_CUDA_P(cudaMemGetInfo(&free_b, &total_b));
+  size_t max_slots = std::max<size_t>(1, (free_b / 2) / (p->slot_doubles * sizeof(double)));
+  p->grid = (int)std::min<size_t>((size_t)p->sm_count * per_sm, max_slots);
+  p->workspace_bytes = (size_t)p->grid * p->slot_doubles * sizeof(double);
+  GSN_CUDA_P(cudaMalloc(&p->d_workspace, p->workspace_bytes));
+  GSN_CUDA_P(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+#undef GSN_CUDA_P
+  *out = p;
+  return GSN_OK;
+}
+
+int gsn_problem_destroy(gsn_problem* p) {
+  if (!p) return GSN_OK;
+  DeviceGuard guard(p->device);
+  cudaFree(p->d_x); cudaFree(p->d_y); cudaFree(p->d_yerr2); cudaFree(p->d_img); cudaFree(p->d_band);
+  cudaFree(p->d_theta_col); cudaFree(p->d_theta_fixed); cudaFree(p->d_workspace); cudaFree(p->d_counter);
+  cudaFree(p->d_theta); cudaFree(p->d_logl); cudaFree(p->d_info);
+  if (p->h_theta) cudaFreeHost(p->h_theta);
+  if (p->h_logl) cudaFreeHost(p->h_logl);
+  if (p->h_info) cudaFreeHost(p->h_info);
+  if (p->own_stream) cudaStreamDestroy(p->own_stream);
+  delete p;
+  return GSN_OK;
+}
+
+int gsn_problem_set_theta_map(gsn_problem* p, const int32_t* col_of_param, const double* fixed_values) {
+  if (!p) return fail(GSN_ERR_INVALID, "problem is null");
+  const int P = p->pd.P;
+  std::vector<int> hcol(std::max(P, 1));
+  std::vector<double> hfix(std::max(P, 1), 0.0);
+  int ncols = 0;
+  for (int k = 0; k < P; ++k) {
+    const int c = col_of_param ? col_of_param[k] : k;
+    if (c < -1 || c >= gsn::kMaxTheta) return fail(GSN_ERR_INVALID, "theta map entry %d = %d out of range", k, c);
+    if (c < 0 && !fixed_values) return fail(GSN_ERR_INVALID, "slot %d is fixed but fixed_values is null", k);
+    hcol[k] = c;
+    hfix[k] = fixed_values ? fixed_values[k] : 0.0;
+    ncols = std::max(ncols, c + 1);
+  }
+  DeviceGuard guard(p->device);
+  GSN_CUDA(cudaMemcpy(p->d_theta_col, hcol.data(), sizeof(int) * hcol.size(), cudaMemcpyHostToDevice));
+  GSN_CUDA(cudaMemcpy(p->d_theta_fixed, hfix.data(), sizeof(double) * hfix.size(), cudaMemcpyHostToDevice));
+  p->n_theta_cols = ncols;
+  return GSN_OK;
+}
+
+static int check_batch_args(gsn_problem* p, const void* theta, int64_t B, int64_t ld, const void* logl) {
+  if (!p) return fail(GSN_ERR_INVALID, "problem is null");
+  if (B < 0) return fail(GSN_ERR_INVALID, "B = %lld is negative", (long long)B);
+  if (B > 0x7fffffffLL) return fail(GSN_ERR_INVALID, "B = %lld exceeds 2^31-1 per call", (long long)B);
+  if (B > 0 && (!logl || (!theta && p->n_theta_cols > 0))) return fail(GSN_ERR_INVALID, "theta and logl must be non-null");
+  if (ld < p->n_theta_cols) return fail(GSN_ERR_INVALID, "ld = %lld is smaller than the %d theta columns in use", (long long)ld, p->n_theta_cols);
+  return GSN_OK;
+}
+
+int gsn_logl_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_t ld, double* logl_dev,
+                   int32_t* info_dev, uint32_t flags, void* cuda_stream) {
+  if (int rc = check_batch_args(p, theta_dev, B, ld, logl_dev)) return rc;
+  if (p->pd.mean_kind == GSN_M_HOST) return fail(GSN_ERR_INVALID, "problem uses a host-supplied mean: call gsn_logl_batch_hostmean");
+  if (B == 0) return GSN_OK;
+  DeviceGuard guard(p->device);
+  return dispatch_logl(p, theta_dev, B, ld, nullptr, logl_dev, info_dev, flags, (cudaStream_t)cuda_stream);
+}
+
+int gsn_logl_batch_hostmean(gsn_problem* p, const double* theta_dev, int64_t B, int64_t ld, const double* mean_dev,
+                            double* logl_dev, int32_t* info_dev, uint32_t flags, void* cuda_stream) {
+  if (int rc = check_batch_args(p, theta_dev, B, ld, logl_dev)) return rc;
+  if (p->pd.mean_kind != GSN_M_HOST) return fail(GSN_ERR_INVALID, "problem was not created with GSN_M_HOST");
+  if (B > 0 && !mean_dev) return fail(GSN_ERR_INVALID, "mean_dev is null");
+  if (B == 0) return GSN_OK;
+  DeviceGuard guard(p->device);
+  return dispatch_logl(p, theta_dev, B, ld, mean_dev, logl_dev, info_dev, flags, (cudaStream_t)cuda_stream);
+}
+
+int gsn_lens_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_t ld, double* shifted_dev, double* b_dev,
+                   void* cuda_stream) {
+  if (int rc = check_batch_args(p, theta_dev, B, ld, shifted_dev)) return rc;
+  if (B > 0 && !b_dev) return fail(GSN_ERR_INVALID, "b_dev is null");
+  if (B == 0) return GSN_OK;
+  DeviceGuard guard(p->device);
+  gsn::lens_batch_kernel<<<(unsigned)B, 128, 0, (cudaStream_t)cuda_stream>>>(p->pd, theta_dev, B, ld, shifted_dev, b_dev);
+  GSN_CUDA(cudaGetLastError());
+  p->launches += 1;
+  return GSN_OK;
+}
+
+int gsn_logl_batch_host(gsn_problem* p, const double* theta_host, int64_t B, int64_t ld, double* logl_host,
+                        int32_t* info_host, uint32_t flags) {
+  if (int rc = check_batch_args(p, theta_host, B, ld, logl_host)) return rc;
+  if (p->pd.mean_kind == GSN_M_HOST) return fail(GSN_ERR_INVALID, "problem uses a host-supplied mean: call gsn_logl_batch_hostmean");
+  if (B == 0) return GSN_OK;
+  DeviceGuard guard(p->device);
+  const int64_t ldc = std::max<int64_t>(ld, 1);
+  if (B > p->stage_rows || ldc != p->stage_ld) {   // (re)size the pinned and device staging buffers
+    cudaFree(p->d_theta); cudaFree(p->d_logl); cudaFree(p->d_info);
+    if (p->h_theta) cudaFreeHost(p->h_theta);
+    if (p->h_logl) cudaFreeHost(p->h_logl);
+    if (p->h_info) cudaFreeHost(p->h_info);
+    p->d_theta = nullptr; p->d_logl = nullptr; p->d_info = nullptr; p->h_theta = nullptr; p->h_logl = nullptr; p->h_info = nullptr;
+    p->stage_rows = 0;
+    const int64_t rows = std::max<int64_t>(B, 1024);
+    GSN_CUDA(cudaMalloc(&p->d_theta, sizeof(double) * rows * ldc));
+    GSN_CUDA(cudaMalloc(&p->d_logl, sizeof(double) * rows));
+    GSN_CUDA(cudaMalloc(&p->d_info, sizeof(int) * rows));
+    GSN_CUDA(cudaMallocHost(&p->h_theta, sizeof(double) * rows * ldc));
+    GSN_CUDA(cudaMallocHost(&p->h_logl, sizeof(double) * rows));
+    GSN_CUDA(cudaMallocHost(&p->h_info, sizeof(int) * rows));
+    p->stage_rows = rows; p->stage_ld = ldc;
+  }
+  cudaStream_t st = p->own_stream;
+  if (ld > 0) std::memcpy(p->h_theta, theta_host, sizeof(double) * B * ld);
+  GSN_CUDA(cudaMemcpyAsync(p->d_theta, p->h_theta, sizeof(double) * B * ldc, cudaMemcpyHostToDevice, st));
+  if (int rc = dispatch_logl(p, p->d_theta, B, ldc, nullptr, p->d_logl, p->d_info, flags, st)) return rc;
+  GSN_CUDA(cudaMemcpyAsync(p->h_logl, p->d_logl, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+  GSN_CUDA(cudaMemcpyAsync(p->h_info, p->d_info, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+  GSN_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(logl_host, p->h_logl, sizeof(double) * B);
+  if (info_host) std::memcpy(info_host, p->h_info, sizeof(int) * B);
+  return GSN_OK;
+}
+
+int64_t gsn_query(const gsn_problem* p, int32_t what) {
+  if (!p) return -1;
+  switch (what) {
+    case GSN_Q_N: return p->pd.N;
+    case GSN_Q_NPARAMS: return p->pd.P;
+    case GSN_Q_NPARAMS_KERNEL: return p->pd.nk;
+    case GSN_Q_NPARAMS_MEAN: return p->pd.nm;
+    case GSN_Q_NPARAMS_LENS: return p->pd.nl;
+    case GSN_Q_WORKSPACE_BYTES: return (int64_t)p->workspace_bytes;
+    case GSN_Q_GRID: return p->grid;
+    case GSN_Q_DEVICE: return p->device;
+    case GSN_Q_LAUNCHES: return p->launches;
+    case GSN_Q_NPAD: return p->pd.Npad;
+    case GSN_Q_PATH: return GSN_PATH_DMMA_BLOCKED;
+  }
+  return -1;
+}
+
+// ---------------------------------------------------------------------------
+// single-call plugin evaluations (host pointers)
+// ---------------------------------------------------------------------------
+static int open_device(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(GSN_ERR_CUDA, "no CUDA device available; libgsn has no CPU path");
+  if (device < 0 || device >= ndev) return fail(GSN_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+  return GSN_OK;
+}
+
+int gsn_covariance(int device, int32_t kernel_kind, const double* params, int32_t n_params, const double* x, int64_t n,
+                   const double* x_prime, int64_t m, double* K_out) {
+  const int need = gsn::kernel_nparams(kernel_kind);
+  if (need < 0) return fail(GSN_ERR_INVALID, "unknown kernel kind %d", kernel_kind);
+  if (n_params < need || (need > 0 && !params)) return fail(GSN_ERR_INVALID, "kernel kind %d needs %d parameters", kernel_kind, need);
+  if (!x || !K_out || n < 1) return fail(GSN_ERR_INVALID, "x and K_out must be non-null, n >= 1");
+  if (!x_prime) { x_prime = x; m = n; }
+  if (m < 1) return fail(GSN_ERR_INVALID, "m must be >= 1");
+  if (kernel_kind == GSN_K_JJ && n != m) return fail(GSN_ERR_INVALID, "JJKernel needs len(x) == len(x_prime) (kernels.py:555)");
+  if (int rc = open_device(device)) return rc;
+  DeviceGuard guard(device);
+  DevBuf dk, dx, dxp, dK;
+  GSN_CUDA(dk.alloc(sizeof(double) * gsn::kMaxKernelParams));
+  GSN_CUDA(dx.alloc(sizeof(double) * n));
+  GSN_CUDA(dxp.alloc(sizeof(double) * m));
+  GSN_CUDA(dK.alloc(sizeof(double) * n * m));
+  double kp[gsn::kMaxKernelParams] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < need; ++i) kp[i] = params[i];
+  GSN_CUDA(cudaMemcpy(dk.p, kp, sizeof kp, cudaMemcpyHostToDevice));
+  GSN_CUDA(cudaMemcpy(dx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+  GSN_CUDA(cudaMemcpy(dxp.p, x_prime, sizeof(double) * m, cudaMemcpyHostToDevice));
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((n * m + threads - 1) / threads, 148 * 16);
+  switch (kernel_kind) {
+#define GSN_CASE(K) case K: covariance_kernel<K><<<blocks, threads>>>(dk.as<double>(), dx.as<double>(), n, dxp.as<double>(), m, dK.as<double>()); break
+    GSN_CASE(GSN_K_EXPSQUARED); GSN_CASE(GSN_K_EXPONENTIAL); GSN_CASE(GSN_K_CONSTANT); GSN_CASE(GSN_K_DOTPRODUCT);
+    GSN_CASE(GSN_K_MATERN32); GSN_CASE(GSN_K_MATERN52); GSN_CASE(GSN_K_RATQUAD); GSN_CASE(GSN_K_GIBBS);
+    GSN_CASE(GSN_K_OU); GSN_CASE(GSN_K_PERIODIC); GSN_CASE(GSN_K_JJ);
+#undef GSN_CASE
+  }
+  GSN_CUDA(cudaGetLastError());
+  GSN_CUDA(cudaMemcpy(K_out, dK.p, sizeof(double) * n * m, cudaMemcpyDeviceToHost));
+  return GSN_OK;
+}
+
+int gsn_mean(int device, int32_t mean_kind, const double* params, int32_t n_params, const double* t, int64_t n,
+             double* mean_out) {
+  const int need = gsn::mean_nparams(mean_kind);
+  if (need < 0 || mean_kind == GSN_M_HOST) return fail(GSN_ERR_INVALID, "mean kind %d cannot be evaluated on the device", mean_kind);
+  if (n_params < need || !params) return fail(GSN_ERR_INVALID, "mean kind %d needs %d parameters", mean_kind, need);
+  if (!t || !mean_out || n < 1) return fail(GSN_ERR_INVALID, "t and mean_out must be non-null, n >= 1");
+  if (int rc = open_device(device)) return rc;
+  DeviceGuard guard(device);
+  DevBuf dm, dt, dout;
+  GSN_CUDA(dm.alloc(sizeof(double) * gsn::kMaxMeanParams));
+  GSN_CUDA(dt.alloc(sizeof(double) * n));
+  GSN_CUDA(dout.alloc(sizeof(double) * n));
+  double mp[gsn::kMaxMeanParams] = {0};
+  for (int i = 0; i < need; ++i) mp[i] = params[i];
+  GSN_CUDA(cudaMemcpy(dm.p, mp, sizeof mp, cudaMemcpyHostToDevice));
+  GSN_CUDA(cudaMemcpy(dt.p, t, sizeof(double) * n, cudaMemcpyHostToDevice));
+  mean_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 1184), 256>>>(mean_kind, dm.as<double>(), dt.as<double>(), n, dout.as<double>());
+  GSN_CUDA(cudaGetLastError());
+  GSN_CUDA(cudaMemcpy(mean_out, dout.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return GSN_OK;
+}
+
+int gsn_lens(int device, int32_t lens_kind, const double* params, int32_t n_params, const double* x, int64_t N,
+             int32_t n_bands, int32_t n_images, const int64_t* indices, double* shifted_out, double* b_out) {
+  const int per = gsn::lens_nparams_per_image(lens_kind);
+  if (per < 0) return fail(GSN_ERR_INVALID, "unknown lensing kind %d", lens_kind);
+  if (n_bands < 1 || n_images < 1 || n_images > gsn::kMaxImages) return fail(GSN_ERR_INVALID, "bad n_bands / n_images");
+  const int need = per * (n_images - 1);
+  if (n_params < need || (need > 0 && !params)) return fail(GSN_ERR_INVALID, "lensing kind %d with %d images needs %d parameters", lens_kind, n_images, need);
+  if (!x || !shifted_out || !b_out || N < 1) return fail(GSN_ERR_INVALID, "x, shifted_out, b_out must be non-null, N >= 1");
+  if (int rc = check_indices(indices, n_bands, n_images, N)) return rc;
+  if (int rc = open_device(device)) return rc;
+  DeviceGuard guard(device);
+  std::vector<int> himg(N, 0);
+  for (int b = 0; b < n_bands; ++b)
+    for (int im = 0; im < n_images; ++im)
+      for (int64_t i = indices[b * n_images + im]; i < indices[b * n_images + im + 1]; ++i) himg[i] = im;
+  DevBuf dl, dimg, dx, ds, db;
+  GSN_CUDA(dl.alloc(sizeof(double) * std::max(need, 1)));
+  GSN_CUDA(dimg.alloc(sizeof(int) * N));
+  GSN_CUDA(dx.alloc(sizeof(double) * N));
+  GSN_CUDA(ds.alloc(sizeof(double) * N));
+  GSN_CUDA(db.alloc(sizeof(double) * N));
+  if (need > 0) GSN_CUDA(cudaMemcpy(dl.p, params, sizeof(double) * need, cudaMemcpyHostToDevice));
+  GSN_CUDA(cudaMemcpy(dimg.p, himg.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
+  GSN_CUDA(cudaMemcpy(dx.p, x, sizeof(double) * N, cudaMemcpyHostToDevice));
+  lens_kernel<<<(int)std::min<int64_t>((N + 255) / 256, 1184), 256>>>(lens_kind, dl.as<double>(), dimg.as<int>(), dx.as<double>(), N, ds.as<double>(), db.as<double>());
+  GSN_CUDA(cudaGetLastError());
+  GSN_CUDA(cudaMemcpy(shifted_out, ds.p, sizeof(double) * N, cudaMemcpyDeviceToHost));
+  GSN_CUDA(cudaMemcpy(b_out, db.p, sizeof(double) * N, cudaMemcpyDeviceToHost));
+  return GSN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+/*
+ * gsn.h -- C ABI of the B200-native batched GP log-likelihood engine (libgsn.so).
+ *
+ * This is the drop-in boundary for the one hot path of erinhay/GausSN: the GP
+ * log-likelihood that the nested/MCMC sampler evaluates for many parameter
+ * vectors theta.  The reference has no FFI of its own (it is pure Python on
+ * JAX); each entry point below names the reference interface it stands in for
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; no torch/CUDA types in the signatures (a CUDA stream
+ *     is passed as void*);
+ *   - every function returns 0 on success and a negative gsn_status on misuse
+ *     or CUDA failure; the message is available from gsn_last_error()
+ *     (thread-local);
+ *   - a numerical failure for one theta (covariance not positive definite, NaN
+ *     in the inputs) is a VALUE, never an error code: logl[i] is NaN (or -inf
+ *     with GSN_FLAG_NEG_INF, which is what GP.jointprobability returns,
+ *     gaussn/gausSN.py:203-204) and info[i] != 0;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     fails with GSN_ERR_CUDA.
+ */
+#ifndef GSN_H_
+#define GSN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSN_ABI_VERSION 1
+
+typedef struct gsn_problem gsn_problem;
+
+typedef enum gsn_status {
+  GSN_OK = 0,
+  GSN_ERR_INVALID = -1,   /* bad argument (null pointer, size, unknown kind, unsorted indices) */
+  GSN_ERR_CUDA = -2,      /* CUDA runtime failure (no device, out of memory, launch failure) */
+  GSN_ERR_UNSUPPORTED = -3
+} gsn_status;
+
+/* Covariance functions: gaussn/kernels.py.  theta slots in constructor order. */
+typedef enum gsn_kernel_kind {
+  GSN_K_EXPSQUARED = 0,   /* kernels.py:4-56     [A, tau]                  A^2 exp(-d^2 / (2 tau^2)) */
+  GSN_K_EXPONENTIAL = 1,  /* kernels.py:58-111   [A, tau]                  A^2 exp(-|d| / tau) */
+  GSN_K_CONSTANT = 2,     /* kernels.py:113-158  [c]                       c */
+  GSN_K_DOTPRODUCT = 3,   /* kernels.py:160-197  []                        x_i x_j */
+  GSN_K_MATERN32 = 4,     /* kernels.py:199-252  [A, l]                    A (1 + s) exp(-s), s = sqrt(3 d^2)/l */
+  GSN_K_MATERN52 = 5,     /* kernels.py:254-309  [A, l]                    A (1 + s + 5 d^2/(3 l^2)) exp(-s), s = sqrt(5 d^2)/l */
+  GSN_K_RATQUAD = 6,      /* kernels.py:311-367  [A, tau, alpha]           A^2 (1 + d^2/(2 alpha tau^2))   (as written) */
+  GSN_K_GIBBS = 7,        /* kernels.py:369-448  [A, lambda, p, mu, sigma] */
+  GSN_K_OU = 8,           /* kernels.py:450-500  [A, l]                    A exp(-|d| / l) */
+  GSN_K_PERIODIC = 9,     /* kernels.py:502-527  [A, l, p]                 A exp(-2 (sin(pi |d| / p) / l)^2) */
+  GSN_K_JJ = 10,          /* kernels.py:529-559  [A, l, m, b]              period m x_j + b from the column epoch; symmetrised */
+  GSN_K_COUNT = 11
+} gsn_kernel_kind;
+
+/* Mean functions: gaussn/meanfuncs.py. */
+typedef enum gsn_mean_kind {
+  GSN_M_UNIFORM = 0,      /* meanfuncs.py:4-45     [c] */
+  GSN_M_SIN = 1,          /* meanfuncs.py:123-172  [A, w, phi] */
+  GSN_M_GAUSSIAN = 2,     /* meanfuncs.py:174-224  [A, mu, sigma] */
+  GSN_M_EXPFUNCTION = 3,  /* meanfuncs.py:226-273  [A, tau] */
+  GSN_M_BAZIN2009 = 4,    /* meanfuncs.py:275-337  [A, beta, t0, Tfall, Trise] */
+  GSN_M_KARPENKA2012 = 5, /* meanfuncs.py:339-408  [lnA, lnB, t1, t0, Tfall, Trise, (ignored ...)] */
+  GSN_M_VILLAR2019 = 6,   /* meanfuncs.py:410-484  [A, beta, t1, t0, Tfall, Trise] */
+  GSN_M_HOST = 7,         /* mean supplied by the caller per theta (sncosmoMean, meanfuncs.py:47-121): see gsn_logl_batch_hostmean */
+  GSN_M_COUNT = 8
+} gsn_mean_kind;
+
+/* Lensing models: gaussn/lensingmodels.py.  Parameters are interleaved per extra
+ * image (image 1 is the reference image with delta = 0, beta = 1). */
+typedef enum gsn_lens_kind {
+  GSN_L_NONE = 0,         /* lensingmodels.py:5-14     no params; no band mask (mask = 1) */
+  GSN_L_CONSTANT = 1,     /* lensingmodels.py:16-118   [delta, beta] x (n_images - 1) */
+  GSN_L_SIGMOID = 2,      /* lensingmodels.py:120-241  [delta, beta0, beta1, r, t0] x (n_images - 1) */
+  GSN_L_SINUSOIDAL = 3,   /* lensingmodels.py:243-364  [delta, beta0, beta1, t0, T] x (n_images - 1) */
+  GSN_L_COUNT = 4
+} gsn_lens_kind;
+
+/* flags for gsn_logl_batch* */
+#define GSN_FLAG_NEG_INF 1u  /* map NaN / +-inf results to -inf (GP.jointprobability, gausSN.py:203-204) */
+
+/* gsn_query selectors */
+typedef enum gsn_query_what {
+  GSN_Q_N = 0,               /* number of epochs */
+  GSN_Q_NPARAMS = 1,         /* full theta width: kernel + mean + lensing */
+  GSN_Q_NPARAMS_KERNEL = 2,
+  GSN_Q_NPARAMS_MEAN = 3,
+  GSN_Q_NPARAMS_LENS = 4,
+  GSN_Q_WORKSPACE_BYTES = 5, /* device workspace owned by the handle */
+  GSN_Q_GRID = 6,            /* persistent CTAs launched per batch call */
+  GSN_Q_DEVICE = 7,
+  GSN_Q_LAUNCHES = 8,        /* kernels launched through this handle so far */
+  GSN_Q_NPAD = 9,            /* padded matrix order used on the device */
+  GSN_Q_PATH = 10            /* which device path the handle dispatches to (gsn_path) */
+} gsn_query_what;
+
+typedef enum gsn_path {
+  GSN_PATH_DMMA_BLOCKED = 1  /* one CTA per theta, blocked left-looking Cholesky, FP64 DMMA updates, L in a global workspace */
+} gsn_path;
+
+/*
+ * Create a problem: one data set (x, y, yerr, segment layout) and one plugin
+ * triple.  Stands in for the state GP.optimize_parameters builds before it
+ * starts a sampler: gaussn/gausSN.py:276-291 (arrays to the device,
+ * _prepare_indices :74-101, lensingmodel.import_from_gp lensingmodels.py:102-118).
+ *
+ *   x, y, yerr  host arrays of N doubles; rows must already be sorted by
+ *               (band, image) exactly as _prepare_indices assumes.  Copied.
+ *   indices     host array of n_bands*n_images + 1 cumulative row counts,
+ *               band-major / image-minor, indices[0] == 0, indices[last] == N.
+ *   n_mean_params  len(meanfunc.params) (Karpenka2012 may carry extra, unused
+ *               entries: meanfuncs.py:357-362); pass -1 for the class default.
+ *               For GSN_M_HOST it is the number of theta slots reserved for the
+ *               host-evaluated mean function (they are skipped on the device).
+ */
+int gsn_problem_create(gsn_problem** out, int device, int64_t N,
+                       const double* x, const double* y, const double* yerr,
+                       int32_t n_bands, int32_t n_images, const int64_t* indices,
+                       int32_t kernel_kind, int32_t mean_kind, int32_t lens_kind,
+                       int32_t n_mean_params);
+
+int gsn_problem_destroy(gsn_problem* p);
+
+/*
+ * fix_* handling of GP.jointprobability (gaussn/gausSN.py:173-194) without
+ * host-side theta expansion.  col_of_param[k] is the column of the caller's
+ * theta matrix that feeds full-theta slot k (order kernel | mean | lensing), or
+ * -1 when slot k is held fixed at fixed_values[k].  Default: identity.
+ */
+int gsn_problem_set_theta_map(gsn_problem* p, const int32_t* col_of_param, const double* fixed_values);
+
+/*
+ * Batched GP.loglikelihood (gaussn/gausSN.py:135-160): logl[i] for each row of
+ * theta.  DEVICE pointers, caller-owned; asynchronous on `cuda_stream`.
+ *
+ *   theta_dev  [B, ld] row-major doubles, ld >= number of mapped columns
+ *   logl_dev   [B] doubles
+ *   info_dev   [B] int32 or NULL: 0 ok; k > 0 the k-th pivot (1-based) was not
+ *              positive; -1 the result is not finite for another reason
+ */
+int gsn_logl_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_t ld,
+                   double* logl_dev, int32_t* info_dev, uint32_t flags, void* cuda_stream);
+
+/* The same call with HOST buffers: pinned staging, H2D of theta and D2H of the
+ * results inside, synchronous.  This is the end-to-end path bench.py times. */
+int gsn_logl_batch_host(gsn_problem* p, const double* theta_host, int64_t B, int64_t ld,
+                        double* logl_host, int32_t* info_host, uint32_t flags);
+
+/* As gsn_logl_batch for a problem created with GSN_M_HOST (a mean function
+ * that only exists on the host, e.g. sncosmoMean, meanfuncs.py:47-121):
+ * mean_dev is [B, N] row-major and holds m(shifted_x) for each theta, evaluated
+ * by the caller at the shifted epochs gsn_lens_batch returns; the device applies
+ * the magnification, mean = b * m (gausSN.py:142), and everything after it. */
+int gsn_logl_batch_hostmean(gsn_problem* p, const double* theta_dev, int64_t B, int64_t ld,
+                            const double* mean_dev, double* logl_dev, int32_t* info_dev,
+                            uint32_t flags, void* cuda_stream);
+
+/* Shifted epochs and magnifications for each theta (what lensingmodel.lens
+ * returns, lensingmodels.py:79-100), so that a host mean function can be
+ * evaluated at the shifted epochs.  shifted_dev and b_dev are [B, N]. */
+int gsn_lens_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_t ld,
+                   double* shifted_dev, double* b_dev, void* cuda_stream);
+
+int64_t gsn_query(const gsn_problem* p, int32_t what);
+
+/* ---- single-call plugin evaluations (HOST pointers, synchronous) ------------ */
+
+/* kernel.covariance(x, x_prime, params): gaussn/kernels.py (each class's
+ * _covariance).  K_out is [n, m] row-major.  x_prime == NULL means x_prime = x.
+ * GSN_K_JJ is returned as written (asymmetric) and needs n == m. */
+int gsn_covariance(int device, int32_t kernel_kind, const double* params, int32_t n_params,
+                   const double* x, int64_t n, const double* x_prime, int64_t m, double* K_out);
+
+/* meanfunc.mean(t, params): gaussn/meanfuncs.py. */
+int gsn_mean(int device, int32_t mean_kind, const double* params, int32_t n_params,
+             const double* t, int64_t n, double* mean_out);
+
+/* lensingmodel.lens(x, params) after import_from_gp: gaussn/lensingmodels.py.
+ * For GSN_L_NONE b_out is filled with 1. */
+int gsn_lens(int device, int32_t lens_kind, const double* params, int32_t n_params,
+             const double* x, int64_t N, int32_t n_bands, int32_t n_images, const int64_t* indices,
+             double* shifted_out, double* b_out);
+
+/* number of theta slots of a plugin (-1 for an unknown kind) */
+int32_t gsn_kernel_nparams(int32_t kernel_kind);
+int32_t gsn_mean_nparams(int32_t mean_kind);
+int32_t gsn_lens_nparams(int32_t lens_kind, int32_t n_images);
+
+int32_t gsn_abi_version(void);
+const char* gsn_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSN_H_ */
