@@ -82,7 +82,7 @@ int launch_logl(gsn_problem* p, const double* theta, int64_t B, int64_t ld, cons
   GSN_CUDA(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned), stream));
   const int grid = (int)std::min<int64_t>(B, p->grid);
   kern<<<grid, gsn::kThreads, p->smem_bytes, stream>>>(p->pd, theta, B, ld, hostmean, logl, info, flags,
-                                                      p->d_workspace, p->slot_doubles, p->d_counter);
+                                                      p->d_workspace, p->d_counter);
   GSN_CUDA(cudaGetLastError());
   p->launches += 1;
   return GSN_OK;
@@ -119,7 +119,7 @@ __global__ void covariance_kernel(const double* __restrict__ kp, const double* _
     // JJ: the period is _p(x)[j], i.e. taken from the FIRST argument at the column index (kernels.py:555)
     const double ai = gsn::kernel_has_aux<KIND>() ? gsn::kernel_aux<KIND>(kc, xi) : 0.0;
     const double aj = gsn::kernel_has_aux<KIND>() ? gsn::kernel_aux<KIND>(kc, KIND == GSN_K_JJ ? x[j] : xj) : 0.0;
-    K[idx] = gsn::cov_elem<KIND>(kc, xi, xj, ai, aj);
+    K[idx] = gsn::cov_elem<KIND>(kc, xi, xj, ai, aj, gsn::kExp2Tab);
   }
 }
 
@@ -175,7 +175,7 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
                        int32_t mean_kind, int32_t lens_kind, int32_t n_mean_params) {
   if (!out) return fail(GSN_ERR_INVALID, "out is null");
   *out = nullptr;
-  if (N < 1 || N > (1 << 20)) return fail(GSN_ERR_INVALID, "N = %lld out of range", (long long)N);
+  if (N < 1 || N > 32 * (gsn::kMaxChunks - 1)) return fail(GSN_ERR_INVALID, "N = %lld out of range (1..%d)", (long long)N, 32 * (gsn::kMaxChunks - 1));
   if (!x || !y || !yerr) return fail(GSN_ERR_INVALID, "x, y and yerr must be non-null");
   if (n_bands < 1 || n_images < 1) return fail(GSN_ERR_INVALID, "n_bands and n_images must be >= 1");
   if (n_images > gsn::kMaxImages) return fail(GSN_ERR_UNSUPPORTED, "at most %d images are supported", gsn::kMaxImages);
@@ -208,6 +208,7 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   pd.Npad = (int)((N + 31) / 32 * 32);
   pd.nblk = pd.Npad / 32;
   pd.n_images = n_images;
+  pd.n_bands = n_bands;
   pd.mean_kind = mean_kind;
   pd.lens_kind = lens_kind;
   pd.use_mask = (lens_kind != GSN_L_NONE) ? 1 : 0;  // NoLensing.mask = 1 (lensingmodels.py:10)

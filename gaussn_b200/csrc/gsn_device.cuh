@@ -17,6 +17,49 @@ constexpr int kMaxImages = 16;
 constexpr int kMaxLensPerImage = 5;
 constexpr int kMaxTheta = kMaxKernelParams + kMaxMeanParams + kMaxLensPerImage * (kMaxImages - 1);
 
+// ---------------------------------------------------------------------------
+// exp() for the N^2 covariance build.  libdevice's exp costs ~22 DFMA-equivalents
+// per element (measured, profiles/r01_fp64_peaks.json), i.e. ~12% on top of the
+// Cholesky at N = 512.  This one reduces with a 64-entry table of 2^(j/64) and a
+// degree-5 polynomial: x = (64 k + j) ln2/64 + r, |r| <= ln2/128,
+// exp(x) = 2^k * T[j] * (1 + p(r)); truncation error r^6/720 < 4e-17, total error
+// about 1 ulp.  Results below 2^-1021 (x < -708) are flushed to zero.
+// ---------------------------------------------------------------------------
+__constant__ double kExp2Tab[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+
+__device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab) {
+  if (!(x >= -708.0)) return (x != x) ? x : 0.0;   // NaN stays NaN; deep underflow -> 0
+  if (x > 709.0) return exp(x);
+  const double t = fma(x, 0x1.71547652b82fep+6, 6755399441055744.0);   // x * 64/ln2, rounded to nearest integer
+  const int n = __double2loint(t);
+  const double nf = t - 6755399441055744.0;
+  double r = fma(nf, -0x1.62e42fee00000p-7, x);
+  r = fma(nf, -0x1.a39ef35793c76p-39, r);
+  double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p * r, r, r);                       // r + r^2/2 + r^3/6 + r^4/24 + r^5/120
+  const double T = tab[n & 63];
+  const double v = fma(T, p, T);
+  return __longlong_as_double(__double_as_longlong(v) + ((long long)(n >> 6) << 52));
+}
+
 __host__ __device__ inline int kernel_nparams(int kind) {
   switch (kind) {
     case GSN_K_EXPSQUARED: case GSN_K_EXPONENTIAL: case GSN_K_MATERN32: case GSN_K_MATERN52: case GSN_K_OU: return 2;
@@ -50,8 +93,15 @@ __host__ __device__ inline int lens_nparams_per_image(int kind) {
 
 // ---------------------------------------------------------------------------
 // Covariance functions.  KernelConsts holds what depends on theta only, computed
-// once per theta; cov_elem() is the per-element work.  `aux` is a per-epoch
-// quantity hoisted out of the N^2 loop (Gibbs: tau(x), JJ: the period p(x)).
+// once per theta (reciprocals included, so that the N^2 loop has no division);
+// cov_elem() is the per-element work.  `aux` is a per-epoch quantity hoisted out
+// of the N^2 loop (Gibbs: tau(x), JJ: 1 / p(x)).
+//
+// Deviation from the reference's operation order, by design: the reference
+// divides per element (e.g. -d^2 / (2 tau^2)); here the divisor's reciprocal is
+// formed once per theta and multiplied in, and sqrt(c d^2) is evaluated as
+// sqrt(c) |d|.  Each changes an exponent by at most ~2 ulp, i.e. a covariance
+// entry by |exponent| * 2^-52 relative -- the same order as exp()'s own rounding.
 // ---------------------------------------------------------------------------
 struct KernelConsts {
   double amp;  // leading factor (A^2, A or c)
@@ -69,16 +119,22 @@ __device__ __forceinline__ KernelConsts kernel_consts(const double* kp) {
     c.c1 = 1.0 / (2.0 * (kp[1] * kp[1]));
   } else if (KIND == GSN_K_EXPONENTIAL) { // kernels.py:109-110   A**2 * exp(-sqrt(d**2)/tau)
     c.amp = kp[0] * kp[0];
-    c.c1 = kp[1];
+    c.c1 = 1.0 / kp[1];
   } else if (KIND == GSN_K_CONSTANT) {    // kernels.py:157
     c.amp = kp[0];
-  } else if (KIND == GSN_K_MATERN32 || KIND == GSN_K_MATERN52 || KIND == GSN_K_OU) {  // :250-251, :305-308, :498-499
+  } else if (KIND == GSN_K_MATERN32) {    // kernels.py:250-251   A (1 + s) exp(-s), s = sqrt(3 d^2)/l
     c.amp = kp[0];
-    c.c1 = kp[1];
-    c.c2 = 3.0 * (kp[1] * kp[1]);         // Matern52: 3*(l**2)
+    c.c1 = sqrt(3.0) / kp[1];
+  } else if (KIND == GSN_K_MATERN52) {    // kernels.py:305-308   s = sqrt(5 d^2)/l, + 5 d^2/(3 l^2)
+    c.amp = kp[0];
+    c.c1 = sqrt(5.0) / kp[1];
+    c.c2 = 5.0 / (3.0 * (kp[1] * kp[1]));
+  } else if (KIND == GSN_K_OU) {          // kernels.py:498-499   A exp(-sqrt(d^2)/l)
+    c.amp = kp[0];
+    c.c1 = 1.0 / kp[1];
   } else if (KIND == GSN_K_RATQUAD) {     // kernels.py:366   A**2 * (1 + d**2/(2*alpha*tau**2))
     c.amp = kp[0] * kp[0];
-    c.c1 = 2.0 * kp[2] * (kp[1] * kp[1]);
+    c.c1 = 1.0 / (2.0 * kp[2] * (kp[1] * kp[1]));
   } else if (KIND == GSN_K_GIBBS) {       // kernels.py:438-447
     c.amp = kp[0] * kp[0];
     c.c1 = kp[1];                          // lambda
@@ -87,11 +143,11 @@ __device__ __forceinline__ KernelConsts kernel_consts(const double* kp) {
     c.c4 = kp[4];                          // sigma
   } else if (KIND == GSN_K_PERIODIC) {    // kernels.py:523-526
     c.amp = kp[0];
-    c.c1 = kp[1];                          // l
-    c.c2 = kp[2];                          // p
+    c.c1 = 1.0 / kp[1];                    // 1 / l
+    c.c2 = 1.0 / kp[2];                    // 1 / p
   } else if (KIND == GSN_K_JJ) {          // kernels.py:552-558
     c.amp = kp[0];
-    c.c1 = kp[1];                          // l
+    c.c1 = 1.0 / kp[1];                    // 1 / l
     c.c2 = kp[2];                          // m
     c.c3 = kp[3];                          // b
   }
@@ -111,46 +167,45 @@ __device__ __forceinline__ double kernel_aux(const KernelConsts& c, double x) {
     const double normal = exp(-(d * d) / (2.0 * (sigma * sigma))) / (sigma * sqrt(2.0 * M_PI));
     return c.c1 * (1.0 - (c.c2 * normal));
   }
-  if (KIND == GSN_K_JJ) return c.c2 * x + c.c3;  // _p(x), kernels.py:549-550
+  if (KIND == GSN_K_JJ) return 1.0 / (c.c2 * x + c.c3);  // 1 / _p(x), kernels.py:549-550
   return 0.0;
 }
 
 // k(x_i, x_j) as the reference's _covariance writes element [i, j].  For the JJ
 // kernel the period comes from the column epoch j (kernels.py:555 broadcasting),
-// so the value is not symmetric in (i, j).
+// so the value is not symmetric in (i, j).  `tab` is the 2^(j/64) table of
+// fast_exp (shared memory in the hot kernel).
 template <int KIND>
-__device__ __forceinline__ double cov_elem(const KernelConsts& c, double xi, double xj, double auxi, double auxj) {
+__device__ __forceinline__ double cov_elem(const KernelConsts& c, double xi, double xj, double auxi, double auxj,
+                                           const double* __restrict__ tab) {
   const double d = xi - xj;
   if (KIND == GSN_K_EXPSQUARED) {
-    return c.amp * exp(-(d * d) * c.c1);
-  } else if (KIND == GSN_K_EXPONENTIAL) {
-    return c.amp * exp(-sqrt(d * d) / c.c1);
+    return c.amp * fast_exp(-(d * d) * c.c1, tab);
+  } else if (KIND == GSN_K_EXPONENTIAL || KIND == GSN_K_OU) {
+    return c.amp * fast_exp(-fabs(d) * c.c1, tab);
   } else if (KIND == GSN_K_CONSTANT) {
     return c.amp;
   } else if (KIND == GSN_K_DOTPRODUCT) {   // kernels.py:196
     return xi * xj;
   } else if (KIND == GSN_K_MATERN32) {
-    const double s = sqrt(3.0 * (d * d)) / c.c1;
-    return c.amp * ((1.0 + s) * exp(-s));
+    const double s = fabs(d) * c.c1;
+    return c.amp * ((1.0 + s) * fast_exp(-s, tab));
   } else if (KIND == GSN_K_MATERN52) {
-    const double r2 = d * d;
-    const double s = sqrt(5.0 * r2) / c.c1;
-    const double a = 1.0 + s + (5.0 * r2 / c.c2);
-    return c.amp * a * exp(-s);
+    const double s = fabs(d) * c.c1;
+    const double a = 1.0 + s + ((d * d) * c.c2);
+    return c.amp * a * fast_exp(-s, tab);
   } else if (KIND == GSN_K_RATQUAD) {
-    return c.amp * (1.0 + (d * d) / c.c1);
+    return c.amp * (1.0 + (d * d) * c.c1);
   } else if (KIND == GSN_K_GIBBS) {
     const double root_num = 2.0 * auxi * auxj;
-    const double denom = (auxi * auxi) + (auxj * auxj);
-    return c.amp * sqrt(root_num / denom) * exp(-(d * d) / denom);
-  } else if (KIND == GSN_K_OU) {
-    return c.amp * exp(-sqrt(d * d) / c.c1);
+    const double inv = 1.0 / ((auxi * auxi) + (auxj * auxj));
+    return c.amp * sqrt(root_num * inv) * fast_exp(-(d * d) * inv, tab);
   } else if (KIND == GSN_K_PERIODIC) {
-    const double s = sin(M_PI * (sqrt(d * d) / c.c2)) / c.c1;
-    return c.amp * exp(-2.0 * (s * s));
+    const double s = sin(M_PI * (fabs(d) * c.c2)) * c.c1;
+    return c.amp * fast_exp(-2.0 * (s * s), tab);
   } else if (KIND == GSN_K_JJ) {
-    const double s = sin(M_PI * (sqrt(d * d) / auxj)) / c.c1;
-    return c.amp * exp(-2.0 * (s * s));
+    const double s = sin(M_PI * (fabs(d) * auxj)) * c.c1;
+    return c.amp * fast_exp(-2.0 * (s * s), tab);
   }
   return 0.0;
 }
@@ -158,11 +213,12 @@ __device__ __forceinline__ double cov_elem(const KernelConsts& c, double xi, dou
 // The value that enters the factorisation: (cov + cov^T)/2, the symmetrisation
 // jnp.linalg.cholesky applies (gausSN.py:150).  Only JJ is asymmetric.
 template <int KIND>
-__device__ __forceinline__ double cov_elem_sym(const KernelConsts& c, double xi, double xj, double auxi, double auxj) {
+__device__ __forceinline__ double cov_elem_sym(const KernelConsts& c, double xi, double xj, double auxi, double auxj,
+                                               const double* __restrict__ tab) {
   if (KIND == GSN_K_JJ) {
-    return 0.5 * (cov_elem<KIND>(c, xi, xj, auxi, auxj) + cov_elem<KIND>(c, xj, xi, auxj, auxi));
+    return 0.5 * (cov_elem<KIND>(c, xi, xj, auxi, auxj, tab) + cov_elem<KIND>(c, xj, xi, auxj, auxi, tab));
   }
-  return cov_elem<KIND>(c, xi, xj, auxi, auxj);
+  return cov_elem<KIND>(c, xi, xj, auxi, auxj, tab);
 }
 
 // ---------------------------------------------------------------------------
