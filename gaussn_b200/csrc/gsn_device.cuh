@@ -43,21 +43,46 @@ __constant__ double kExp2Tab[64] = {
     0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
     0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
 
+// Polynomial and reduction constants live in constant memory so that the FP64
+// instructions take them as constant-bank operands instead of rebuilding each
+// 64-bit immediate with two moves per use.
+__constant__ double kExpC[8] = {
+    0x1.71547652b82fep+6,    // 64 / ln 2
+    6755399441055744.0,      // 1.5 * 2^52: round-to-nearest-integer trick
+    -0x1.62e42fee00000p-7,   // -(ln 2 / 64), high part (32 significant bits)
+    -0x1.a39ef35793c76p-39,  // -(ln 2 / 64), low part
+    1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+
+// Branch-free core: the caller guarantees x is not NaN (the hot kernel checks the
+// kernel constants and the shifted epochs once per theta).  Results that would be
+// subnormal (x < -708.4) are flushed to zero, overflow gives +inf.
 __device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab) {
-  if (!(x >= -708.0)) return (x != x) ? x : 0.0;   // NaN stays NaN; deep underflow -> 0
-  if (x > 709.0) return exp(x);
-  const double t = fma(x, 0x1.71547652b82fep+6, 6755399441055744.0);   // x * 64/ln2, rounded to nearest integer
+  const double t = fma(x, kExpC[0], kExpC[1]);
   const int n = __double2loint(t);
-  const double nf = t - 6755399441055744.0;
-  double r = fma(nf, -0x1.62e42fee00000p-7, x);
-  r = fma(nf, -0x1.a39ef35793c76p-39, r);
-  double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-  p = fma(p, r, 1.0 / 6.0);
-  p = fma(p, r, 0.5);
+  const double nf = t - kExpC[1];
+  double r = fma(nf, kExpC[2], x);
+  r = fma(nf, kExpC[3], r);
+  double p = fma(r, kExpC[4], kExpC[5]);
+  p = fma(p, r, kExpC[6]);
+  p = fma(p, r, kExpC[7]);
   p = fma(p * r, r, r);                       // r + r^2/2 + r^3/6 + r^4/24 + r^5/120
   const double T = tab[n & 63];
-  const double v = fma(T, p, T);
-  return __longlong_as_double(__double_as_longlong(v) + ((long long)(n >> 6) << 52));
+  const double v = fma(T, p, T);              // in [1, 2)
+  const int k = n >> 6;
+  int hi = __double2hiint(v) + (k << 20);
+  int lo = __double2loint(v);
+  // |x| >= 708 (or +-inf): underflow is flushed to zero, overflow saturates to +inf
+  const int xh = __double2hiint(x);
+  if ((xh & 0x7fffffff) >= 0x40862000) {
+    if (xh < 0) return 0.0;
+    if (x > 709.782712893384) return __hiloint2double(0x7ff00000, 0);
+  }
+  return __hiloint2double(hi, lo);
+}
+
+// Full-range wrapper for callers that cannot rule out NaN.
+__device__ __forceinline__ double fast_exp_checked(double x, const double* __restrict__ tab) {
+  return (x != x) ? x : fast_exp(x, tab);
 }
 
 __host__ __device__ inline int kernel_nparams(int kind) {
@@ -113,7 +138,7 @@ struct KernelConsts {
 
 template <int KIND>
 __device__ __forceinline__ KernelConsts kernel_consts(const double* kp) {
-  KernelConsts c{0.0, 0.0, 0.0, 0.0, 0.0};
+  KernelConsts c{1.0, 0.0, 0.0, 0.0, 0.0};
   if (KIND == GSN_K_EXPSQUARED) {         // kernels.py:55   A**2 * exp(-d**2/(2*tau**2))
     c.amp = kp[0] * kp[0];
     c.c1 = 1.0 / (2.0 * (kp[1] * kp[1]));
@@ -175,50 +200,65 @@ __device__ __forceinline__ double kernel_aux(const KernelConsts& c, double x) {
 // kernel the period comes from the column epoch j (kernels.py:555 broadcasting),
 // so the value is not symmetric in (i, j).  `tab` is the 2^(j/64) table of
 // fast_exp (shared memory in the hot kernel).
+// cov_unit is the covariance without its leading amplitude factor (c.amp), which the
+// hot kernel folds into a per-column coefficient.  The arguments handed to fast_exp
+// are finite-or-infinite but never NaN as long as the kernel constants and the
+// epochs are finite, which the hot kernel checks once per theta.
 template <int KIND>
-__device__ __forceinline__ double cov_elem(const KernelConsts& c, double xi, double xj, double auxi, double auxj,
+__device__ __forceinline__ double cov_unit(const KernelConsts& c, double xi, double xj, double auxi, double auxj,
                                            const double* __restrict__ tab) {
   const double d = xi - xj;
   if (KIND == GSN_K_EXPSQUARED) {
-    return c.amp * fast_exp(-(d * d) * c.c1, tab);
+    return fast_exp(-(d * d) * c.c1, tab);
   } else if (KIND == GSN_K_EXPONENTIAL || KIND == GSN_K_OU) {
-    return c.amp * fast_exp(-fabs(d) * c.c1, tab);
+    return fast_exp(-fabs(d) * c.c1, tab);
   } else if (KIND == GSN_K_CONSTANT) {
-    return c.amp;
+    return 1.0;
   } else if (KIND == GSN_K_DOTPRODUCT) {   // kernels.py:196
     return xi * xj;
   } else if (KIND == GSN_K_MATERN32) {
     const double s = fabs(d) * c.c1;
-    return c.amp * ((1.0 + s) * fast_exp(-s, tab));
+    return (1.0 + s) * fast_exp(-s, tab);
   } else if (KIND == GSN_K_MATERN52) {
     const double s = fabs(d) * c.c1;
     const double a = 1.0 + s + ((d * d) * c.c2);
-    return c.amp * a * fast_exp(-s, tab);
+    return a * fast_exp(-s, tab);
   } else if (KIND == GSN_K_RATQUAD) {
-    return c.amp * (1.0 + (d * d) * c.c1);
+    return 1.0 + (d * d) * c.c1;
   } else if (KIND == GSN_K_GIBBS) {
     const double root_num = 2.0 * auxi * auxj;
     const double inv = 1.0 / ((auxi * auxi) + (auxj * auxj));
-    return c.amp * sqrt(root_num * inv) * fast_exp(-(d * d) * inv, tab);
+    return sqrt(root_num * inv) * fast_exp_checked(-(d * d) * inv, tab);
   } else if (KIND == GSN_K_PERIODIC) {
     const double s = sin(M_PI * (fabs(d) * c.c2)) * c.c1;
-    return c.amp * fast_exp(-2.0 * (s * s), tab);
+    return fast_exp_checked(-2.0 * (s * s), tab);
   } else if (KIND == GSN_K_JJ) {
     const double s = sin(M_PI * (fabs(d) * auxj)) * c.c1;
-    return c.amp * fast_exp(-2.0 * (s * s), tab);
+    return fast_exp_checked(-2.0 * (s * s), tab);
   }
   return 0.0;
 }
 
-// The value that enters the factorisation: (cov + cov^T)/2, the symmetrisation
-// jnp.linalg.cholesky applies (gausSN.py:150).  Only JJ is asymmetric.
+// (cov + cov^T)/2 without the amplitude: the symmetrisation jnp.linalg.cholesky applies
+// (gausSN.py:150).  Only JJ is asymmetric.
 template <int KIND>
-__device__ __forceinline__ double cov_elem_sym(const KernelConsts& c, double xi, double xj, double auxi, double auxj,
+__device__ __forceinline__ double cov_unit_sym(const KernelConsts& c, double xi, double xj, double auxi, double auxj,
                                                const double* __restrict__ tab) {
   if (KIND == GSN_K_JJ) {
-    return 0.5 * (cov_elem<KIND>(c, xi, xj, auxi, auxj, tab) + cov_elem<KIND>(c, xj, xi, auxj, auxi, tab));
+    return 0.5 * (cov_unit<KIND>(c, xi, xj, auxi, auxj, tab) + cov_unit<KIND>(c, xj, xi, auxj, auxi, tab));
   }
-  return cov_elem<KIND>(c, xi, xj, auxi, auxj, tab);
+  return cov_unit<KIND>(c, xi, xj, auxi, auxj, tab);
+}
+
+// Full covariance element (single-call API path; NaN-safe).
+template <int KIND>
+__device__ __forceinline__ double cov_elem(const KernelConsts& c, double xi, double xj, double auxi, double auxj,
+                                           const double* __restrict__ tab) {
+  const double u = cov_unit<KIND>(c, xi, xj, auxi, auxj, tab);
+  const double d = xi - xj;
+  // the branch-free exp core does not propagate NaN: restore it for arbitrary user input
+  if (d != d || c.c1 != c.c1 || c.c2 != c.c2) return d + c.c1 + c.c2;
+  return c.amp * u;
 }
 
 // ---------------------------------------------------------------------------
