@@ -3,7 +3,7 @@
 Follows SURVEY.md section 8(d): S = n_bands * n_images segments of N // S epochs
 (remainder on the last), epochs sorted uniform on [0, T] per segment with image
 i > 1 offset by its true delay, fluxes drawn once from the model's own GP prior
-at a "truth" theta and scaled to unit range, errors uniform(0.005, 0.03), and
+(random Fourier features) at a "truth" theta and scaled to unit range, errors uniform(0.005, 0.03), and
 theta batches uniform in the notebooks' prior boxes
 (ipynb/fitting_SLSN_example.ipynb cell "ptform": A in [0,1], tau in [10,40],
 delta in [0,60], beta in [0.1,1]).  Seeds: data 20240530, theta 20240531.
@@ -52,14 +52,18 @@ def make_dataset(N: int, n_bands: int = 1, n_images: int = 2, span: float = 150.
             image += [f"image_{i + 1}"] * n
     x, xs, bvec = np.concatenate(x), np.concatenate(xs), np.concatenate(bvec)
     band, image = np.array(band), np.array(image)
-    # one draw from the GP prior at the truth (ExpSquared, per band independent), magnified per image
+    # One draw from (a random-Fourier-feature approximation of) the ExpSquared GP prior at the truth,
+    # independent per band, magnified per image.  Only elementwise operations are used, so the data are
+    # reproducible across machines to the last ulp or two (a dense eigen-decomposition of the nearly
+    # singular prior covariance is not: its null-space vectors depend on the BLAS build).
+    M = 512
     y = np.empty(N)
     for b in range(n_bands):
         sel = band == f"band_{b}"
-        d = xs[sel][:, None] - xs[sel][None, :]
-        K = truth_A**2 * np.exp(-d**2 / (2 * truth_tau**2)) + 1e-10 * np.eye(sel.sum())
-        w, V = np.linalg.eigh(K)
-        f = V @ (np.sqrt(np.clip(w, 0, None)) * rng.standard_normal(sel.sum()))
+        omega = rng.standard_normal(M) / truth_tau
+        phase = rng.uniform(0.0, 2.0 * np.pi, M)
+        amp = truth_A * np.sqrt(2.0 / M)
+        f = amp * np.cos(np.outer(xs[sel], omega) + phase[None, :]).sum(axis=1)
         y[sel] = bvec[sel] * (truth_c + f)
     yerr = rng.uniform(0.005, 0.03, N)
     scale = y.max() - y.min()

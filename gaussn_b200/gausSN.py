@@ -243,6 +243,13 @@ class GP:
             raise ValueError(f"theta has {width} columns, expected {ncols} (kernel | mean | lensing minus fixed groups)")
         return self._evaluate(theta, _engine.FLAG_NEG_INF if neg_inf else 0)
 
+    def loglikelihood_batch_sharded(self, theta, group=None, **kwargs):
+        """``loglikelihood_batch`` with the rows of ``theta`` split over the ranks of a
+        torch.distributed group (one process per GPU) and the results all-gathered; every
+        rank passes the same ``theta`` and receives the full vector."""
+        from . import sharding
+        return sharding.evaluate_sharded(lambda th: self.loglikelihood_batch(th, **kwargs), theta, group)
+
     def jointprobability(self, params, logprior=None, fix_kernel_params=False, fix_mean_params=False,
                          fix_lensing_params=False, invert=1):
         """``invert * (logL + log prior)``; NaN / inf become ``invert * -inf``

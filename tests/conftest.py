@@ -52,7 +52,7 @@ def libgsn():
     return _engine.load()
 
 
-def assert_logl_close(got, want, what=""):
+def assert_logl_close(got, want, what="", atol=LOGL_ATOL, rtol=LOGL_RTOL):
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
     assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
@@ -63,7 +63,7 @@ def assert_logl_close(got, want, what=""):
     fin = ~(nan_w | inf_w)
     if fin.any():
         err = np.abs(got[fin] - want[fin])
-        tol = np.maximum(LOGL_ATOL, LOGL_RTOL * np.abs(want[fin]))
+        tol = np.maximum(atol, rtol * np.abs(want[fin]))
         worst = int(np.argmax(err / tol))
         assert np.all(err <= tol), (f"{what}: max |dlogL| = {err.max():.3e} (worst: got {got[fin][worst]!r}, "
                                     f"want {want[fin][worst]!r}, tol {tol[worst]:.1e})")

@@ -59,3 +59,244 @@ def test_logl_cases_against_reference_vectors(libgsn, golden):
             print("LARGE", row["dataset"], row["kernel"], row["mean"], row["lensing"], got[-1], want[-1])
     assert_logl_close(got, want, "logl")
     assert_logl_close(gotj, wantj, "jointprobability")
+
+
+# --------------------------------------------------------------------------- plugin single calls
+def test_plugin_covariance_mean_lens_against_reference_vectors(libgsn, golden):
+    from gaussn_b200 import kernels, meanfuncs, lensingmodels
+    for row in golden["cov"]:
+        k = kernels.DotProductKernel() if row["kernel"] == "DotProductKernel" else getattr(kernels, row["kernel"])(row["params"])
+        K = k.covariance(np.array(row["x"]), x_prime=None if row.get("x_prime") is None else np.array(row["x_prime"]))
+        assert list(K.shape) == row["shape"]
+        # The device multiplies by per-theta reciprocals instead of dividing per element, so an
+        # exponent e = ln(K / amplitude) carries ~2 ulp: relative error of the entry ~ (|e| + 3) * 2^-51.
+        want = np.array(row["K"])
+        nz = want != 0
+        depth = np.abs(np.log(np.abs(want[nz]) / np.abs(want).max()))
+        rel = np.abs(K.ravel()[nz] - want[nz]) / np.abs(want[nz])
+        assert np.all(rel <= (depth + 3.0) * 2.0**-51), (row["kernel"], rel.max())
+        assert np.all(np.abs(K.ravel()[~nz]) <= 1e-300)
+    for row in golden["mean"]:
+        m = getattr(meanfuncs, row["mean"])(row["params"]).mean(np.array(row["t"]))
+        np.testing.assert_allclose(m, row["m"], rtol=2e-14, atol=1e-300, err_msg=row["mean"])
+    for row in golden["lens"]:
+        lm = getattr(lensingmodels, row["lensing"])(row["params"])
+        lm.import_from_gp(row["n_bands"], row["n_images"], np.array(row["indices"]))
+        xs, b = lm.lens(np.array(row["x"]))
+        np.testing.assert_array_equal(xs, row["shifted_x"])
+        want_b = np.array(row["b"])
+        np.testing.assert_array_equal(np.isnan(b), np.isnan(want_b))
+        np.testing.assert_allclose(b[~np.isnan(b)], want_b[~np.isnan(b)], rtol=2e-14, atol=0)
+        np.testing.assert_array_equal(lm.mask.ravel(), row["mask"])
+
+
+def test_theta_slicing_under_fix_flags(libgsn, golden):
+    """All eight fix_* combinations and both signs of `invert` (gausSN.py:173-206)."""
+    ds = golden["logl_datasets"]["s2x2"]
+    for row in golden["slicing"]:
+        gp = make_gp(ds, "ExpSquaredKernel", row["kernel0"], "UniformMean", row["mean0"], "ConstantMagnification", row["lens0"])
+        got = gp.jointprobability(row["theta"], (lambda v: (lambda p: v))(row["logprior"]), row["fix_kernel"], row["fix_mean"],
+                                  row["fix_lens"], row["invert"])
+        assert_logl_close([got], [row["value"]], f"slicing {row['fix_kernel']}{row['fix_mean']}{row['fix_lens']}")
+
+
+def test_predict_against_reference_vectors(libgsn, golden):
+    from gaussn_b200 import gausSN, kernels, meanfuncs
+    for row in golden["predict"]:
+        ds = golden["logl_datasets"][row["dataset"]]
+        gp = gausSN.GP(getattr(kernels, row["kernel"])(row["kernel_params"]), getattr(meanfuncs, row["mean"])(row["mean_params"]))
+        e, v = gp.predict(np.array(row["x_prime"]), np.array(ds["x"]), np.array(ds["y"]), np.array(ds["yerr"]))
+        np.testing.assert_allclose(e, row["expectation"], rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(v.ravel(), row["variance"], rtol=1e-8, atol=1e-10)
+
+
+# --------------------------------------------------------------------------- seeded sweeps against the oracle
+def _synth(rng, N, n_bands, n_images, span=120.0):
+    S = n_bands * n_images
+    counts = [N // S] * S
+    counts[-1] += N - sum(counts)
+    x, band, image = [], [], []
+    for b in range(n_bands):
+        for i in range(n_images):
+            n = counts[b * n_images + i]
+            x.append(np.sort(rng.uniform(0, span, n)) + 9.0 * i)
+            band += [f"b{b}"] * n
+            image += [f"i{i}"] * n
+    x = np.concatenate(x) if N else np.zeros(0)
+    y = 0.4 + 0.3 * np.sin(x / 15.0) + 0.04 * rng.standard_normal(N)
+    yerr = rng.uniform(0.02, 0.06, N)
+    return dict(x=x, y=y, yerr=yerr, band=np.array(band), image=np.array(image))
+
+
+def _theta_box(rng, B, kernel, mean, lens, n_images):
+    kbox = {"ExpSquaredKernel": [(0.05, 0.6), (3, 12)], "ExponentialKernel": [(0.05, 0.6), (3, 30)], "ConstantKernel": [(0.01, 0.3)],
+            "Matern32Kernel": [(0.01, 0.3), (3, 30)], "Matern52Kernel": [(0.01, 0.3), (3, 20)], "OUKernel": [(0.01, 0.3), (3, 40)],
+            "GibbsKernel": [(0.05, 0.5), (5, 15), (0.1, 0.6), (40, 80), (15, 30)], "PeriodicKernel": [(0.01, 0.2), (0.8, 2.0), (20, 50)],
+            "RationalQuadraticKernel": [(0.005, 0.02), (400, 600), (1.5, 3.0)], "JJKernel": [(0.005, 0.02), (1.0, 2.0), (1e-5, 1e-4), (25, 40)]}
+    mbox = {"UniformMean": [(0.2, 0.7)], "Sin": [(0.1, 0.4), (0.05, 0.08), (-0.5, 0.5)], "Gaussian": [(5, 25), (40, 70), (15, 30)],
+            "ExpFunction": [(0.2, 0.6), (-0.004, 0.004)], "Bazin2009": [(0.5, 2), (0, 0.2), (20, 40), (25, 50), (4, 10)],
+            "Karpenka2012": [(-1.5, 0), (-9, -7), (20, 50), (20, 40), (25, 50), (4, 10)],
+            "Villar2019": [(0.3, 0.8), (-0.004, 0.0), (40, 80), (10, 30), (20, 40), (3, 8)]}
+    lbox = {"NoLensing": [], "ConstantMagnification": [(0, 25), (0.4, 1.6)],
+            "SigmoidMagnification": [(0, 25), (0.4, 1.2), (-0.3, 0.3), (0.02, 0.3), (30, 90)]}
+    cols = [rng.uniform(lo, hi, B) for lo, hi in kbox[kernel] + mbox[mean]]
+    for _ in range(n_images - 1):
+        cols += [rng.uniform(lo, hi, B) for lo, hi in lbox[lens]]
+    return np.column_stack(cols)
+
+
+def _oracle_batch(ds, theta, kernel, mean, lens, gp):
+    return gp_oracle.loglikelihood_batch(theta, ds["x"], ds["y"], ds["yerr"], kernel, mean, lens, gp.n_bands, gp.n_images, gp.indices)
+
+
+def _gp_for(ds, kernel, mean, lens, n_images, theta_row):
+    nk, nm = gp_oracle.KERNEL_NPARAMS[kernel], gp_oracle.MEAN_NPARAMS[mean]
+    return make_gp(ds, kernel, theta_row[:nk], mean, theta_row[nk:nk + nm], lens, theta_row[nk + nm:])
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 7, 31, 32, 33, 63, 64, 65, 96, 141, 194, 257, 429, 512])
+def test_sizes_around_tile_boundaries(libgsn, N):
+    """Ragged and tiny inputs: the device pads to a multiple of 32 with identity rows."""
+    rng = np.random.default_rng(1000 + N)
+    n_images = 2 if N >= 2 else 1
+    ds = _synth(rng, N, 1, n_images)
+    theta = _theta_box(rng, 24, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", n_images)
+    gp = _gp_for(ds, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", n_images, theta[0])
+    got = gp.loglikelihood_batch(theta)
+    assert_logl_close(got, _oracle_batch(ds, theta, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", gp), f"N={N}")
+
+
+@pytest.mark.parametrize("kernel", ["ExpSquaredKernel", "ExponentialKernel", "ConstantKernel", "Matern32Kernel", "Matern52Kernel",
+                                    "OUKernel", "GibbsKernel", "PeriodicKernel", "RationalQuadraticKernel", "JJKernel"])
+def test_every_kernel_multiband_multiimage(libgsn, kernel):
+    rng = np.random.default_rng(abs(hash(kernel)) % 2**31)
+    ds = _synth(rng, 150, 2, 3)
+    theta = _theta_box(rng, 48, kernel, "UniformMean", "ConstantMagnification", 3)
+    gp = _gp_for(ds, kernel, "UniformMean", "ConstantMagnification", 3, theta[0])
+    want = _oracle_batch(ds, theta, kernel, "UniformMean", "ConstantMagnification", gp)
+    assert_logl_close(gp.loglikelihood_batch(theta), want, kernel)
+    assert np.isfinite(want).sum() >= 24, f"{kernel}: box too hostile, {np.isfinite(want).sum()} finite"
+
+
+@pytest.mark.parametrize("mean", ["UniformMean", "Sin", "Gaussian", "ExpFunction", "Bazin2009", "Karpenka2012", "Villar2019"])
+@pytest.mark.parametrize("lens", ["NoLensing", "ConstantMagnification", "SigmoidMagnification"])
+def test_every_mean_and_lensing_model(libgsn, mean, lens):
+    rng = np.random.default_rng(abs(hash(mean + lens)) % 2**31)
+    n_images = 1 if lens == "NoLensing" else 2
+    ds = _synth(rng, 120, 2, n_images)
+    theta = _theta_box(rng, 32, "Matern32Kernel", mean, lens, n_images)
+    gp = _gp_for(ds, "Matern32Kernel", mean, lens, n_images, theta[0])
+    want = _oracle_batch(ds, theta, "Matern32Kernel", mean, lens, gp)
+    assert_logl_close(gp.loglikelihood_batch(theta), want, mean + "/" + lens)
+
+
+def test_four_images_three_bands_sigmoid_config_c2(libgsn):
+    """BASELINE.json config 2 as SURVEY 8d makes it concrete: 3 bands x 4 images, N = 396, Matern-3/2,
+    sigmoid microlensing, P = 18."""
+    rng = np.random.default_rng(42)
+    ds = _synth(rng, 396, 3, 4)
+    theta = _theta_box(rng, 64, "Matern32Kernel", "UniformMean", "SigmoidMagnification", 4)
+    assert theta.shape[1] == 18
+    gp = _gp_for(ds, "Matern32Kernel", "UniformMean", "SigmoidMagnification", 4, theta[0])
+    assert_logl_close(gp.loglikelihood_batch(theta), _oracle_batch(ds, theta, "Matern32Kernel", "UniformMean", "SigmoidMagnification", gp), "C2")
+
+
+def test_failure_values_per_theta_do_not_abort_the_batch(libgsn):
+    """Non-PD and NaN parameter points give NaN (loglikelihood) / -inf (jointprobability) for that
+    theta only (gausSN.py:203-204); info carries the failing pivot."""
+    from gaussn_b200 import _engine
+    rng = np.random.default_rng(5)
+    ds = _synth(rng, 100, 1, 2)
+    theta = _theta_box(rng, 16, "OUKernel", "UniformMean", "ConstantMagnification", 2)
+    theta[3, 0] = -0.5            # negative amplitude: not positive definite
+    theta[5, 1] = 0.0             # l = 0: NaN covariance
+    theta[7, 2] = np.nan          # NaN mean
+    theta[9, 4] = np.inf          # infinite magnification
+    theta[11, 3] = np.nan         # NaN delay: non-finite shifted epochs
+    gp = _gp_for(ds, "OUKernel", "UniformMean", "ConstantMagnification", 2, theta[0])
+    want = _oracle_batch(ds, theta, "OUKernel", "UniformMean", "ConstantMagnification", gp)
+    got = gp.loglikelihood_batch(theta)
+    assert_logl_close(got, want, "failures")
+    assert set(np.where(np.isnan(got))[0]) == {3, 5, 7, 9, 11}
+    out, info = gp._problem.logl_host(theta, _engine.FLAG_NEG_INF, return_info=True)
+    assert np.all(np.isneginf(out[[3, 5, 7, 9, 11]])) and np.all(info[[3, 5, 7, 9, 11]] != 0)
+    assert np.all(info[np.isfinite(want)] == 0) and info[3] > 0
+    jp = gp.jointprobability_batch(theta, logprior=lambda p: 0.0)
+    np.testing.assert_array_equal(np.isneginf(jp), np.isnan(want))
+
+
+def test_sinusoidal_magnification_is_minus_inf_as_in_the_reference(libgsn):
+    rng = np.random.default_rng(6)
+    ds = _synth(rng, 60, 1, 2)
+    gp = make_gp(ds, "ExpSquaredKernel", [0.3, 10.0], "UniformMean", [0.5], "SinusoidalMagnification", [5.0, 0.8, 0.1, 30.0, 9.0])
+    assert np.isnan(gp.loglikelihood(gp.x, gp.y, gp.yerr, [0.3, 10.0], [0.5], [5.0, 0.8, 0.1, 30.0, 9.0]))
+    assert gp.jointprobability([0.3, 10.0, 0.5, 5.0, 0.8, 0.1, 30.0, 9.0]) == -np.inf
+
+
+def test_host_buffer_and_device_buffer_paths_are_bit_identical(libgsn):
+    import torch
+    rng = np.random.default_rng(8)
+    ds = _synth(rng, 200, 2, 2)
+    theta = _theta_box(rng, 500, "Matern52Kernel", "UniformMean", "ConstantMagnification", 2)
+    gp = _gp_for(ds, "Matern52Kernel", "UniformMean", "ConstantMagnification", 2, theta[0])
+    a = gp.loglikelihood_batch(theta)
+    b = gp.loglikelihood_batch(torch.as_tensor(theta, device="cuda")).cpu().numpy()
+    c = gp.loglikelihood_batch(theta[::-1].copy())[::-1]
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(a, c)        # scheduling order does not change any value
+    assert gp.loglikelihood_batch(np.zeros((0, 5))).shape == (0,)
+
+
+def test_no_lensing_multiband_is_dense(libgsn):
+    """NoLensing.mask is the scalar 1 (lensingmodels.py:10): bands are NOT decoupled."""
+    rng = np.random.default_rng(9)
+    ds = _synth(rng, 90, 3, 1)
+    theta = _theta_box(rng, 8, "ExpSquaredKernel", "UniformMean", "NoLensing", 1)
+    gp = _gp_for(ds, "ExpSquaredKernel", "UniformMean", "NoLensing", 1, theta[0])
+    dense = _oracle_batch(ds, theta, "ExpSquaredKernel", "UniformMean", "NoLensing", gp)
+    assert_logl_close(gp.loglikelihood_batch(theta), dense, "dense")
+    lensed = make_gp(ds, "ExpSquaredKernel", theta[0, :2], "UniformMean", theta[0, 2:3], "ConstantMagnification", [])
+    masked = lensed.loglikelihood_batch(theta)
+    assert np.max(np.abs(masked - dense)) > 1e-3          # the band mask does change the answer
+
+
+def test_host_supplied_mean_path(libgsn):
+    """sncosmoMean-style host mean (meanfuncs.py:47-121) through gsn_lens_batch + gsn_logl_batch_hostmean,
+    with a stand-in model whose bandflux is Bazin2009 so that the oracle can check it."""
+    from gaussn_b200 import gausSN, kernels, meanfuncs, lensingmodels
+
+    class FakeModel:
+        param_names = ["A", "beta", "t0", "Tfall", "Trise"]
+
+        def __init__(self):
+            self.parameters = np.array([1.0, 0.1, 30.0, 40.0, 8.0])
+
+        def update(self, d):
+            for k, v in d.items():
+                self.parameters[self.param_names.index(k)] = v
+
+        def bandflux(self, bands, t, zp=None, zpsys=None):
+            return gp_oracle.mean("Bazin2009", list(self.parameters), t)
+
+    rng = np.random.default_rng(10)
+    ds = _synth(rng, 80, 2, 2)
+    theta = _theta_box(rng, 12, "ExpSquaredKernel", "Bazin2009", "ConstantMagnification", 2)
+    gp = gausSN.GP(kernels.ExpSquaredKernel([0.3, 8.0]), meanfuncs.sncosmoMean(FakeModel()), lensingmodels.ConstantMagnification([5.0, 0.9]))
+    gp.x, gp.y, gp.yerr, gp.bands = ds["x"], ds["y"], ds["yerr"], ds["band"]
+    gp._prepare_indices(ds["x"], ds["band"], ds["image"])
+    got = gp.loglikelihood_batch(theta)
+    want = gp_oracle.loglikelihood_batch(theta, ds["x"], ds["y"], ds["yerr"], "ExpSquaredKernel", "Bazin2009", "ConstantMagnification",
+                                         gp.n_bands, gp.n_images, gp.indices)
+    assert_logl_close(got, want, "host mean")
+
+
+def test_minimize_reaches_the_notebook_optimum_region(libgsn, golden):
+    """Soft end-to-end: optimize_parameters(method='minimize') on simSN_107 from the
+    SLSN-notebook start climbs above the notebook's loglstar = 368.647."""
+    from gaussn_b200 import gausSN, kernels, meanfuncs, lensingmodels
+    ds = golden["datasets"]["simSN_107"]
+    gp = gausSN.GP(kernels.ExpSquaredKernel([0.3, 28.0]), meanfuncs.UniformMean([0.0]), lensingmodels.ConstantMagnification([38.0, 0.5]))
+    res = gp.optimize_parameters(np.array(ds["x"]), np.array(ds["y"]), np.array(ds["yerr"]), band=np.array(ds["band"]),
+                                 image=np.array(ds["image"]), method="minimize", fix_mean_params=True,
+                                 minimize_kwargs=dict(method="Nelder-Mead", options=dict(xatol=1e-4, fatol=1e-6, maxiter=600)))
+    assert -res.fun >= 368.647, res

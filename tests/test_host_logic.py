@@ -1,0 +1,137 @@
+"""CPU: host-side mirror of the reference interface -- plugin classes, segment bookkeeping,
+theta packing, sharding (gloo, world size 2)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_prepare_indices_matches_reference(golden, libgsn):
+    from gaussn_b200 import gausSN, kernels, meanfuncs
+    for row in golden["indices"]:
+        gp = gausSN.GP(kernels.ConstantKernel([1.0]), meanfuncs.UniformMean([0.0]))
+        gp._prepare_indices(np.arange(row["n"], dtype=float), None if row["band"] is None else np.array(row["band"]),
+                            None if row["image"] is None else np.array(row["image"]))
+        assert list(gp.indices) == row["indices"]
+        assert (gp.n_bands, gp.n_images) == (row["n_bands"], row["n_images"])
+        assert gp.factor == pytest.approx(row["factor"], rel=1e-15)
+
+
+def test_plugin_classes_mirror_the_reference_attributes(libgsn):
+    from gaussn_b200 import kernels, meanfuncs, lensingmodels
+    k = kernels.GibbsKernel([1.0, 2.0, 0.3, 4.0, 5.0])
+    assert (k.A, k.lamdba, k.p, k.mu, k.sigma) == (1.0, 2.0, 0.3, 4.0, 5.0) and k.params == [1.0, 2.0, 0.3, 4.0, 5.0]
+    k._reset([9.0, 8.0, 0.7, 6.0, 5.0])
+    assert k.lamdba == 8.0 and k.params[0] == 9.0
+    dp = kernels.DotProductKernel()
+    assert not hasattr(dp, "params") and dp.c == 0
+    dp._reset()
+    m = meanfuncs.Karpenka2012([0.5, -1.0, 3.0, 2.0, 10.0, 2.0, 99.0])
+    assert len(m.params) == 7 and m.A == pytest.approx(np.exp(0.5)) and m.B == pytest.approx(np.exp(-1.0))
+    assert kernels.JJKernel([1.0, 2.0, 0.5, 3.0])._p(2.0) == 4.0
+    lm = lensingmodels.SigmoidMagnification([10.0, 0.5, 0.3, 0.2, 40.0, 25.0, 1.7, -0.4, 0.05, 60.0])
+    np.testing.assert_array_equal(lm.deltas, [0.0, 10.0, 25.0])
+    np.testing.assert_array_equal(lm.beta0s, [1.0, 0.5, 1.7])
+    np.testing.assert_array_equal(lm.t0s, [0.0, 40.0, 60.0])
+    sm = lensingmodels.SinusoidalMagnification([10.0, 0.5, 0.3, 40.0, 9.0])
+    np.testing.assert_array_equal(sm.Ts, [0.0, 9.0])
+    cm = lensingmodels.ConstantMagnification([10.0, 0.5])
+    cm.import_from_gp(2, 2, np.array([0, 2, 3, 5, 6]))
+    np.testing.assert_array_equal(cm.repeats, [2, 1, 2, 1])
+    want = np.zeros((6, 6)); want[:3, :3] = 1; want[3:, 3:] = 1
+    np.testing.assert_array_equal(cm.mask, want)
+    nl = lensingmodels.NoLensing()
+    x = np.arange(3.0)
+    assert nl.mask == 1 and nl.lens(x)[1] == 1 and nl.lens(x)[0] is x
+    with pytest.raises(IndexError):
+        kernels.ExpSquaredKernel([1.0])
+
+
+def test_gp_rejects_plugins_without_a_device_implementation(libgsn):
+    from gaussn_b200 import gausSN, kernels, meanfuncs
+
+    class MyKernel:
+        params = [1.0]
+
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        gausSN.GP(MyKernel(), meanfuncs.UniformMean([0.0]))
+    gp = gausSN.GP(kernels.ExpSquaredKernel([1.0, 2.0]), meanfuncs.UniformMean([0.0]))
+    with pytest.raises(NotImplementedError):
+        gp.optimize_parameters(np.arange(4.0), np.arange(4.0), np.ones(4), loglikelihood=lambda *a: 0.0)
+
+
+def test_initial_position_follows_the_theta_packing_order(libgsn):
+    from gaussn_b200 import gausSN, kernels, meanfuncs, lensingmodels
+    gp = gausSN.GP(kernels.ExpSquaredKernel([1.0, 2.0]), meanfuncs.UniformMean([3.0]), lensingmodels.ConstantMagnification([4.0, 5.0]))
+    assert gp._get_initial_pos(False, False, False) == [1.0, 2.0, 3.0, 4.0, 5.0]
+    assert gp._get_initial_pos(True, False, False) == [3.0, 4.0, 5.0]
+    assert gp._get_initial_pos(False, True, False) == [1.0, 2.0, 4.0, 5.0]
+    assert gp._get_initial_pos(True, True, False) == [4.0, 5.0]
+    with pytest.raises(Exception, match="No parameters"):
+        gp._get_initial_pos(True, True, True)
+
+
+def test_shard_bounds_cover_every_row_exactly_once():
+    from gaussn_b200.sharding import shard_bounds
+    for B in (0, 1, 7, 8, 9, 65536, 65537):
+        for world in (1, 2, 3, 4, 8):
+            seen = np.zeros(B, dtype=int)
+            for r in range(world):
+                a, b, per = shard_bounds(B, world, r)
+                assert 0 <= a <= b <= B and b - a <= per
+                seen[a:b] += 1
+            assert np.all(seen == 1)
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, 2)
+
+
+def _gloo_worker(rank, world, port, B, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from gaussn_b200.sharding import evaluate_sharded, shard_bounds
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(1)
+    theta = rng.normal(size=(B, 5))
+    calls = []
+
+    def evaluate(th):       # stands in for GP.loglikelihood_batch (no GPU here): a row-wise function
+        calls.append(len(th))
+        return np.sin(th).sum(axis=1)
+
+    full = evaluate_sharded(evaluate, theta)
+    a, b, _ = shard_bounds(B, world, rank)
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), full)
+    assert calls == ([b - a] if b > a else [])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [10, 11, 1])
+def test_sharded_evaluation_world_size_2_gloo(tmp_path, B):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() + B) % 2000
+    mp.spawn(_gloo_worker, args=(2, port, B, str(tmp_path)), nprocs=2, join=True)
+    rng = np.random.default_rng(1)
+    want = np.sin(rng.normal(size=(B, 5))).sum(axis=1)
+    for r in range(2):
+        got = np.load(tmp_path / f"r{r}.npy")
+        np.testing.assert_array_equal(got, want)       # bit-identical to the unsharded evaluation
+
+
+def test_bench_flop_model():
+    import benchdata
+    # 44 739 243 + 262 144 + 919 296 flop for N=512, one block, ExpSquared
+    assert benchdata.algorithmic_flops(512, 1, True) == pytest.approx(44739242.67 + 262144 + 919296, rel=1e-9)
+    # block-diagonal by band: never count the masked-out zero blocks
+    assert benchdata.algorithmic_flops(512, 4, True) == pytest.approx(4 * (128**3 / 3 + 128**2 + 7 * 128 * 129 / 2))
+    assert benchdata.algorithmic_flops(512, 4, False) == benchdata.algorithmic_flops(512, 1, True)
+    ds = benchdata.make_dataset(96, 2, 3)
+    assert len(ds["x"]) == 96 and list(ds["indices"]) == [0, 16, 32, 48, 64, 80, 96]
+    for s in range(6):
+        seg = ds["x"][ds["indices"][s]:ds["indices"][s + 1]]
+        assert np.all(np.diff(seg) >= 0)
+    th = benchdata.make_theta(100, 3)
+    assert th.shape == (100, 7) and th[:, 1].min() >= 10 and th[:, 1].max() <= 40
