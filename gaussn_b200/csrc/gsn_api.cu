@@ -55,7 +55,7 @@ struct gsn_problem {
   // device buffers
   double* d_x = nullptr; double* d_y = nullptr; double* d_yerr2 = nullptr;
   int* d_img = nullptr; int* d_band = nullptr;
-  int* d_theta_col = nullptr; double* d_theta_fixed = nullptr;
+  int* d_theta_col = nullptr; double* d_theta_fixed = nullptr; unsigned* d_items = nullptr;
   double* d_workspace = nullptr; size_t slot_doubles = 0; size_t workspace_bytes = 0;
   unsigned* d_counter = nullptr;
   int grid = 0; size_t smem_bytes = 0;
@@ -247,6 +247,14 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   GSN_CUDA_P(cudaMalloc(&p->d_theta_col, sizeof(int) * hcol.size()));
   GSN_CUDA_P(cudaMalloc(&p->d_theta_fixed, sizeof(double) * hfix.size()));
   GSN_CUDA_P(cudaMalloc(&p->d_counter, sizeof(unsigned)));
+  {
+    std::vector<unsigned> items((size_t)pd.nblk * (pd.nblk + 1) / 2);
+    gsn::make_item_order(pd.nblk, items.data());
+    pd.n_items = (int)items.size();
+    GSN_CUDA_P(cudaMalloc(&p->d_items, sizeof(unsigned) * items.size()));
+    GSN_CUDA_P(cudaMemcpy(p->d_items, items.data(), sizeof(unsigned) * items.size(), cudaMemcpyHostToDevice));
+    pd.items = p->d_items;
+  }
   GSN_CUDA_P(cudaMemcpy(p->d_x, hx.data(), nb, cudaMemcpyHostToDevice));
   GSN_CUDA_P(cudaMemcpy(p->d_y, hy.data(), nb, cudaMemcpyHostToDevice));
   GSN_CUDA_P(cudaMemcpy(p->d_yerr2, he.data(), nb, cudaMemcpyHostToDevice));
@@ -280,7 +288,7 @@ int gsn_problem_destroy(gsn_problem* p) {
   if (!p) return GSN_OK;
   DeviceGuard guard(p->device);
   cudaFree(p->d_x); cudaFree(p->d_y); cudaFree(p->d_yerr2); cudaFree(p->d_img); cudaFree(p->d_band);
-  cudaFree(p->d_theta_col); cudaFree(p->d_theta_fixed); cudaFree(p->d_workspace); cudaFree(p->d_counter);
+  cudaFree(p->d_theta_col); cudaFree(p->d_theta_fixed); cudaFree(p->d_workspace); cudaFree(p->d_counter); cudaFree(p->d_items);
   cudaFree(p->d_theta); cudaFree(p->d_logl); cudaFree(p->d_info);
   if (p->h_theta) cudaFreeHost(p->h_theta);
   if (p->h_logl) cudaFreeHost(p->h_logl);
