@@ -42,7 +42,7 @@ _lp = C.POINTER(C.c_int64)
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    return os.environ.get("GSN_LIB", _build.LIB_PATH)   # GSN_LIB: tuning experiments with alternative builds
 
 
 def load():

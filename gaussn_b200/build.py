@@ -13,16 +13,27 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "libgsn.so")
-SOURCES = [os.path.join(PKG_DIR, "csrc", "gsn_api.cu")]
+OBJ_DIR = os.path.join(PKG_DIR, "csrc", "build")
+CSRC = os.path.join(PKG_DIR, "csrc")
 HEADERS = [
-    os.path.join(PKG_DIR, "csrc", "gsn_device.cuh"),
-    os.path.join(PKG_DIR, "csrc", "gsn_chol_dmma.cuh"),
+    os.path.join(CSRC, "gsn_device.cuh"),
+    os.path.join(CSRC, "gsn_chol_dmma.cuh"),
+    os.path.join(CSRC, "gsn_launch.h"),
     os.path.join(REPO_DIR, "include", "gsn.h"),
 ]
+SOURCES = [os.path.join(CSRC, "gsn_api.cu"), os.path.join(CSRC, "gsn_kernels.cu")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
+]
+# translation units: the C ABI plus four slices of kernel instantiations ({shape} x {kinds}), built in parallel
+UNITS = [
+    ("gsn_api", "gsn_api.cu", []),
+    ("gsn_wide_a", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgWide", "-DGSN_SLICE_NAME=launch_logl_wide_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),
+    ("gsn_wide_b", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgWide", "-DGSN_SLICE_NAME=launch_logl_wide_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
+    ("gsn_narrow_a", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgNarrow", "-DGSN_SLICE_NAME=launch_logl_narrow_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),
+    ("gsn_narrow_b", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgNarrow", "-DGSN_SLICE_NAME=launch_logl_narrow_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
 ]
 
 
@@ -44,16 +55,25 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     """Compile libgsn.so if it is missing or older than its sources."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    nvcc = _nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    procs = []
+    for name, src, defs in UNITS:
+        cmd = [nvcc, *NVCC_FLAGS, *defs, "-c", "-o", os.path.join(OBJ_DIR, name + ".o"), os.path.join(CSRC, src)]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+            print(" ".join(cmd))
+        procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for name, proc in procs:
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {name} ({proc.returncode}):\n{out}")
+        if verbose:
+            print(out)
+    objs = [os.path.join(OBJ_DIR, name + ".o") for name, _, _ in UNITS]
+    res = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH, *objs], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError(f"link failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
     return LIB_PATH
 
 

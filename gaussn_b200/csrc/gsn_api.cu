@@ -14,6 +14,7 @@
 #include "../../include/gsn.h"
 #include "gsn_device.cuh"
 #include "gsn_chol_dmma.cuh"
+#include "gsn_launch.h"
 
 namespace {
 
@@ -58,7 +59,7 @@ struct gsn_problem {
   int* d_theta_col = nullptr; double* d_theta_fixed = nullptr; unsigned* d_items = nullptr;
   double* d_workspace = nullptr; size_t slot_doubles = 0; size_t workspace_bytes = 0;
   unsigned* d_counter = nullptr;
-  int grid = 0; size_t smem_bytes = 0;
+  int grid = 0; size_t smem_bytes = 0; bool narrow = false;
   int n_theta_cols = 0;   // columns the caller's theta must provide
   // host staging for gsn_logl_batch_host
   double* h_theta = nullptr; double* h_logl = nullptr; int* h_info = nullptr;
@@ -70,42 +71,18 @@ struct gsn_problem {
 
 namespace {
 
-template <int KIND>
-int launch_logl(gsn_problem* p, const double* theta, int64_t B, int64_t ld, const double* hostmean,
-                double* logl, int* info, unsigned flags, cudaStream_t stream) {
-  static bool attr_set[64] = {};
-  auto kern = gsn::logl_dmma_kernel<KIND>;
-  if (!attr_set[p->device & 63]) {
-    GSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set[p->device & 63] = true;
-  }
-  GSN_CUDA(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned), stream));
-  const int grid = (int)std::min<int64_t>(B, p->grid);
-  kern<<<grid, gsn::kThreads, p->smem_bytes, stream>>>(p->pd, theta, B, ld, hostmean, logl, info, flags,
-                                                      p->d_workspace, p->d_counter);
-  GSN_CUDA(cudaGetLastError());
-  p->launches += 1;
-  return GSN_OK;
-}
-
 int dispatch_logl(gsn_problem* p, const double* theta, int64_t B, int64_t ld, const double* hostmean,
                   double* logl, int* info, unsigned flags, cudaStream_t stream) {
-  switch (p->kernel_kind) {
-#define GSN_CASE(K) case K: return launch_logl<K>(p, theta, B, ld, hostmean, logl, info, flags, stream)
-    GSN_CASE(GSN_K_EXPSQUARED);
-    GSN_CASE(GSN_K_EXPONENTIAL);
-    GSN_CASE(GSN_K_CONSTANT);
-    GSN_CASE(GSN_K_DOTPRODUCT);
-    GSN_CASE(GSN_K_MATERN32);
-    GSN_CASE(GSN_K_MATERN52);
-    GSN_CASE(GSN_K_RATQUAD);
-    GSN_CASE(GSN_K_GIBBS);
-    GSN_CASE(GSN_K_OU);
-    GSN_CASE(GSN_K_PERIODIC);
-    GSN_CASE(GSN_K_JJ);
-#undef GSN_CASE
-  }
-  return fail(GSN_ERR_INVALID, "unknown kernel kind %d", p->kernel_kind);
+  GSN_CUDA(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned), stream));
+  gsn::LaunchArgs a{p->pd, theta, B, ld, hostmean, logl, info, flags, p->d_workspace, p->d_counter,
+                    (int)std::min<int64_t>(B, p->grid), p->smem_bytes, stream};
+  const int k = p->kernel_kind;
+  cudaError_t e;
+  if (p->narrow) e = (k <= 4) ? gsn::launch_logl_narrow_a(k, a) : gsn::launch_logl_narrow_b(k, a);
+  else           e = (k <= 4) ? gsn::launch_logl_wide_a(k, a) : gsn::launch_logl_wide_b(k, a);
+  if (e != cudaSuccess) return fail(GSN_ERR_CUDA, "log-likelihood kernel launch failed: %s", cudaGetErrorString(e));
+  p->launches += 1;
+  return GSN_OK;
 }
 
 template <int KIND>
@@ -266,9 +243,12 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   pd.theta_col = p->d_theta_col; pd.theta_fixed = p->d_theta_fixed;
 
   // persistent grid: CTAs/SM limited by registers (launch bounds) and shared memory
-  p->smem_bytes = gsn::logl_dmma_smem_bytes(pd.Npad);
-  if (p->smem_bytes > 200 * 1024) return cleanup(fail(GSN_ERR_UNSUPPORTED, "N = %lld needs %zu bytes of shared memory", (long long)N, p->smem_bytes));
-  int per_sm = (int)std::min<size_t>(gsn::kMinCtasPerSm, (size_t)(227 * 1024) / (p->smem_bytes + 1024));
+  const bool has_aux = kernel_kind == GSN_K_GIBBS || kernel_kind == GSN_K_JJ;
+  p->narrow = N <= gsn::kNarrowMaxN;    // one warp per theta while a theta has few work items (see CfgNarrow)
+  p->smem_bytes = p->narrow ? gsn::logl_dmma_smem_bytes<gsn::CfgNarrow>(pd.Npad, has_aux) : gsn::logl_dmma_smem_bytes<gsn::CfgWide>(pd.Npad, has_aux);
+  if (p->smem_bytes > 226 * 1024) return cleanup(fail(GSN_ERR_UNSUPPORTED, "N = %lld needs %zu bytes of shared memory", (long long)N, p->smem_bytes));
+  const int cfg_ctas = p->narrow ? gsn::CfgNarrow::kCtasPerSm : gsn::CfgWide::kCtasPerSm;
+  int per_sm = (int)std::min<size_t>(cfg_ctas, (size_t)(227 * 1024) / (p->smem_bytes + 1024));
   per_sm = std::max(per_sm, 1);
   p->slot_doubles = gsn::logl_dmma_slot_doubles(pd.Npad);
   // bound the workspace to a quarter of device memory for very large N
@@ -407,7 +387,7 @@ int64_t gsn_query(const gsn_problem* p, int32_t what) {
     case GSN_Q_DEVICE: return p->device;
     case GSN_Q_LAUNCHES: return p->launches;
     case GSN_Q_NPAD: return p->pd.Npad;
-    case GSN_Q_PATH: return GSN_PATH_DMMA_BLOCKED;
+    case GSN_Q_PATH: return p->narrow ? GSN_PATH_DMMA_BLOCKED_NARROW : GSN_PATH_DMMA_BLOCKED;
   }
   return -1;
 }

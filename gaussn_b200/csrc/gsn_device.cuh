@@ -25,7 +25,7 @@ constexpr int kMaxTheta = kMaxKernelParams + kMaxMeanParams + kMaxLensPerImage *
 // exp(x) = 2^k * T[j] * (1 + p(r)); truncation error r^6/720 < 4e-17, total error
 // about 1 ulp.  Results below 2^-1021 (x < -708) are flushed to zero.
 // ---------------------------------------------------------------------------
-__constant__ double kExp2Tab[64] = {
+static __constant__ double kExp2Tab[64] = {
     0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
     0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
     0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
@@ -46,7 +46,7 @@ __constant__ double kExp2Tab[64] = {
 // Polynomial and reduction constants live in constant memory so that the FP64
 // instructions take them as constant-bank operands instead of rebuilding each
 // 64-bit immediate with two moves per use.
-__constant__ double kExpC[8] = {
+static __constant__ double kExpC[8] = {
     0x1.71547652b82fep+6,    // 64 / ln 2
     6755399441055744.0,      // 1.5 * 2^52: round-to-nearest-integer trick
     -0x1.62e42fee00000p-7,   // -(ln 2 / 64), high part (32 significant bits)

@@ -1,0 +1,38 @@
+// Instantiations of gsn::logl_dmma_kernel.  Compiled four times with
+//   -DGSN_SLICE_CFG={CfgWide|CfgNarrow} -DGSN_SLICE_NAME=... -DGSN_SLICE_LO=.. -DGSN_SLICE_HI=..
+// (see gaussn_b200/build.py) so that the 22 kernel variants build in parallel.
+#include "gsn_launch.h"
+
+namespace gsn {
+
+template <int KIND>
+static cudaError_t launch_one(const LaunchArgs& a) {
+  using Cfg = GSN_SLICE_CFG;
+  auto kern = logl_dmma_kernel<KIND, Cfg>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (!attr_set[dev & 63]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  kern<<<a.grid, Cfg::kWarps * 32, a.smem_bytes, a.stream>>>(a.pd, a.theta, a.B, a.ld, a.hostmean, a.logl, a.info, a.flags,
+                                                            a.workspace, a.counter);
+  return cudaGetLastError();
+}
+
+template <int KIND>
+static cudaError_t dispatch(int kind, const LaunchArgs& a) {
+  if constexpr (KIND > GSN_SLICE_HI) {
+    return cudaErrorInvalidValue;
+  } else {
+    if (kind == KIND) return launch_one<KIND>(a);
+    return dispatch<KIND + 1>(kind, a);
+  }
+}
+
+cudaError_t GSN_SLICE_NAME(int kind, const LaunchArgs& a) { return dispatch<GSN_SLICE_LO>(kind, a); }
+
+}  // namespace gsn

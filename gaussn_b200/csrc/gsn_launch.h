@@ -1,0 +1,31 @@
+// Internal launch interface between the C-ABI translation unit (gsn_api.cu) and the translation
+// units that instantiate the log-likelihood kernel (gsn_kernels.cu, compiled once per slice of
+// {launch shape} x {covariance kinds} so that the slices build in parallel).
+#pragma once
+#include <cuda_runtime.h>
+#include "gsn_chol_dmma.cuh"
+
+namespace gsn {
+
+struct LaunchArgs {
+  ProblemDev pd;
+  const double* theta;
+  long long B, ld;
+  const double* hostmean;
+  double* logl;
+  int* info;
+  unsigned flags;
+  double* workspace;
+  unsigned* counter;
+  int grid;
+  size_t smem_bytes;
+  cudaStream_t stream;
+};
+
+// Each returns cudaSuccess, a CUDA error, or cudaErrorInvalidValue if `kind` is not in its slice.
+cudaError_t launch_logl_wide_a(int kind, const LaunchArgs& a);     // kinds 0..4
+cudaError_t launch_logl_wide_b(int kind, const LaunchArgs& a);     // kinds 5..10
+cudaError_t launch_logl_narrow_a(int kind, const LaunchArgs& a);
+cudaError_t launch_logl_narrow_b(int kind, const LaunchArgs& a);
+
+}  // namespace gsn
