@@ -225,11 +225,24 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   GSN_CUDA_P(cudaMalloc(&p->d_theta_fixed, sizeof(double) * hfix.size()));
   GSN_CUDA_P(cudaMalloc(&p->d_counter, sizeof(unsigned)));
   {
+    // band range of every 32-row chunk (padding rows count as a band of their own) -> first non-zero block column
+    const bool masked = pd.use_mask && n_bands > 1;
+    std::vector<int> lo(pd.nblk), hi(pd.nblk), first_col(pd.nblk, 0);
+    for (int c = 0; c < pd.nblk; ++c) {
+      const int r0 = 32 * c, r1 = 32 * c + 31;
+      lo[c] = r0 < N ? hband[r0] : n_bands;
+      hi[c] = r1 < N ? hband[r1] : n_bands;
+    }
+    if (masked)
+      for (int c = 0; c < pd.nblk; ++c) {
+        int kb = 0;
+        while (kb < c && hi[kb] < lo[c]) ++kb;
+        first_col[c] = kb;
+      }
     std::vector<unsigned> items((size_t)pd.nblk * (pd.nblk + 1) / 2);
-    gsn::make_item_order(pd.nblk, items.data());
-    pd.n_items = (int)items.size();
+    pd.n_items = gsn::make_item_order(pd.nblk, first_col.data(), items.data());
     GSN_CUDA_P(cudaMalloc(&p->d_items, sizeof(unsigned) * items.size()));
-    GSN_CUDA_P(cudaMemcpy(p->d_items, items.data(), sizeof(unsigned) * items.size(), cudaMemcpyHostToDevice));
+    GSN_CUDA_P(cudaMemcpy(p->d_items, items.data(), sizeof(unsigned) * pd.n_items, cudaMemcpyHostToDevice));
     pd.items = p->d_items;
   }
   GSN_CUDA_P(cudaMemcpy(p->d_x, hx.data(), nb, cudaMemcpyHostToDevice));

@@ -300,3 +300,22 @@ def test_minimize_reaches_the_notebook_optimum_region(libgsn, golden):
                                  image=np.array(ds["image"]), method="minimize", fix_mean_params=True,
                                  minimize_kwargs=dict(method="Nelder-Mead", options=dict(xatol=1e-4, fatol=1e-6, maxiter=600)))
     assert -res.fun >= 368.647, res
+
+
+@pytest.mark.parametrize("n_bands,per_band", [(4, 64), (3, 32), (2, 96), (5, 40), (4, 96), (2, 256), (3, 130)])
+def test_band_block_diagonal_structure(libgsn, n_bands, per_band):
+    """With a lensing model the covariance is block diagonal by band (lensingmodels.py:39-51); the engine skips
+    the zero blocks, including the case where band boundaries coincide with its 32-row chunks (then diagonal
+    blocks of different bands are independent and may be factored concurrently), in both launch shapes."""
+    rng = np.random.default_rng(77 + n_bands)
+    ds = _synth(rng, n_bands * per_band, n_bands, 2)
+    theta = _theta_box(rng, 40, "Matern52Kernel", "UniformMean", "ConstantMagnification", 2)
+    gp = _gp_for(ds, "Matern52Kernel", "UniformMean", "ConstantMagnification", 2, theta[0])
+    want = _oracle_batch(ds, theta, "Matern52Kernel", "UniformMean", "ConstantMagnification", gp)
+    assert_logl_close(gp.loglikelihood_batch(theta), want, f"{n_bands} bands x {per_band}")
+    # the same data without a lensing model couples the bands (mask = 1) and must differ
+    theta_nl = theta[:, :3]
+    gp_nl = _gp_for(ds, "Matern52Kernel", "UniformMean", "NoLensing", 1, theta_nl[0])
+    want_nl = gp_oracle.loglikelihood_batch(theta_nl, ds["x"], ds["y"], ds["yerr"], "Matern52Kernel", "UniformMean", "NoLensing",
+                                            gp_nl.n_bands, gp_nl.n_images, gp_nl.indices)
+    assert_logl_close(gp_nl.loglikelihood_batch(theta_nl), want_nl, "dense")
