@@ -10,7 +10,7 @@ Use it the way the reference package is used
 The likelihood runs in hand-written sm_100a CUDA (``libgsn.so``, C ABI in
 ``include/gsn.h``).  There is no CPU implementation in this package.
 """
-from . import _engine, kernels, meanfuncs, lensingmodels, gausSN  # noqa: F401
+from . import _engine, kernels, meanfuncs, lensingmodels, gausSN, samplers, ingest, sharding  # noqa: F401
 from .gausSN import GP  # noqa: F401
 
-__all__ = ["gausSN", "kernels", "meanfuncs", "lensingmodels", "GP"]
+__all__ = ["gausSN", "kernels", "meanfuncs", "lensingmodels", "samplers", "ingest", "sharding", "GP"]

@@ -334,6 +334,14 @@ class GP:
                 raise ImportError("dynesty is not installed")
             nlive = sampler_kwargs.pop('nlive', 500)
             sample = sampler_kwargs.pop('sample', 'rslice')
+            if isinstance(sampler_kwargs.get('pool'), __import__('gaussn_b200.samplers', fromlist=['BatchPool']).BatchPool):
+                # batched queue evaluation: the pool recognises this callable and evaluates whole queues at once
+                from . import samplers
+                post = samplers.VectorizedPosterior(self, *args)
+                sampler_kwargs.setdefault('queue_size', sampler_kwargs['pool'].size)
+                sampler = dynesty.NestedSampler(post, ptform, self.ndim, nlive=nlive, sample=sample, **sampler_kwargs)
+                sampler.run_nested(**run_sampler_kwargs)
+                return sampler
             sampler = dynesty.NestedSampler(self.jointprobability, ptform, self.ndim, logl_args=args, nlive=nlive,
                                             sample=sample, **sampler_kwargs)
             sampler.run_nested(**run_sampler_kwargs)
@@ -348,6 +356,12 @@ class GP:
             if method == 'minimize':
                 if minimize is None:
                     raise ImportError("scipy is not installed")
+                if minimize_kwargs.pop('batched_gradient', False):
+                    # value and forward-difference gradient from one batch of P + 1 points per iteration
+                    from . import samplers
+                    post = samplers.VectorizedPosterior(self, logprior, fix_kernel_params, fix_mean_params, fix_lensing_params, -1)
+                    bounds = minimize_kwargs.get('bounds')
+                    return minimize(lambda th: samplers.fd_value_and_grad(post, th, bounds=bounds), init_pos, jac=True, **minimize_kwargs)
                 return minimize(self.jointprobability, init_pos, args=args + (-1,), **minimize_kwargs)
 
             if np.any(np.isinf(logprior(init_pos))):
@@ -360,14 +374,20 @@ class GP:
             for r, row in enumerate(p0):
                 while np.isinf(logprior(row)):
                     p0[r] = row = np.random.normal(init_pos, 0.001)
+            # both ensemble samplers accept vectorize=True: the whole half-ensemble is one GPU batch per step
+            from . import samplers
+            post = samplers.VectorizedPosterior(self, *args)
+            sampler_kwargs.setdefault('vectorize', True)
+            logprob = post if sampler_kwargs['vectorize'] else self.jointprobability
+            extra = {} if sampler_kwargs['vectorize'] else {'args': args + (1,)}
             if method == 'emcee':
                 if emcee is None:
                     raise ImportError("emcee is not installed")
-                sampler = emcee.EnsembleSampler(nwalkers, self.ndim, self.jointprobability, args=args + (1,), **sampler_kwargs)
+                sampler = emcee.EnsembleSampler(nwalkers, self.ndim, logprob, **extra, **sampler_kwargs)
             else:
                 if zeus is None:
                     raise ImportError("zeus is not installed")
-                sampler = zeus.EnsembleSampler(nwalkers, self.ndim, self.jointprobability, args=list(args) + [1], **sampler_kwargs)
+                sampler = zeus.EnsembleSampler(nwalkers, self.ndim, logprob, **extra, **sampler_kwargs)
             sampler.run_mcmc(p0, nsteps=nsteps, **run_sampler_kwargs)
             return sampler
         raise ValueError(f"unknown method {method!r}")
