@@ -57,11 +57,11 @@ def test_loaders_reproduce_the_golden_datasets(golden):
     d = ingest.load_glsn_csv(f"{REF_DATA}/glSN_forGP_sims/simSN_107.csv")
     g = golden["datasets"]["simSN_107"]
     # the golden arrays were parsed by pandas' fast float parser, which may be one ulp off the correctly
-    # rounded value Python's float() gives: compare to 2 ulp
+    # rounded value Python's float() gives: flux, its range and their quotient each add one: compare to a few ulp
     for k in ("x", "y", "yerr"):
-        np.testing.assert_allclose(d[k], g[k], rtol=4.5e-16, atol=0)
+        np.testing.assert_allclose(d[k], g[k], rtol=2e-15, atol=0)
     assert list(d["band"]) == g["band"] and list(d["image"]) == g["image"]
-    assert d["rescale"] == pytest.approx(g["rescale"], rel=4.5e-16)
+    assert d["rescale"] == pytest.approx(g["rescale"], rel=2e-15)
     q = ingest.load_cosmograil(f"{REF_DATA}/COSMOGRAIL/DES_J0408-5354.txt", telescope="EulerCAM")
     gq = golden["datasets"]["J0408_euler"]
     np.testing.assert_allclose(q["x"], gq["x"], rtol=4.5e-16); np.testing.assert_allclose(q["y"], gq["y"], rtol=1e-15)
