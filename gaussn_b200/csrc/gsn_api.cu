@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <new>
 #include <string>
@@ -196,6 +197,9 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   pd.nlog2pi = (double)N * std::log(2.0 * M_PI);
   p->n_theta_cols = pd.P;
 
+  // one warp per theta while a theta has few work items (see CfgNarrow); GSN_FORCE_SHAPE=narrow|wide is a tuning hook
+  p->narrow = N <= gsn::kNarrowDispatchN;
+  if (const char* shape_env = getenv("GSN_FORCE_SHAPE")) p->narrow = (shape_env[0] == 'n') && N <= gsn::kNarrowMaxN;
   // per-epoch tables (padded)
   std::vector<double> hx(pd.Npad, 0.0), hy(pd.Npad, 0.0), he(pd.Npad, 1.0);
   std::vector<int> himg(pd.Npad, 0), hband(pd.Npad, -1);
@@ -240,7 +244,15 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
         first_col[c] = kb;
       }
     std::vector<unsigned> items((size_t)pd.nblk * (pd.nblk + 1) / 2);
-    pd.n_items = gsn::make_item_order(pd.nblk, first_col.data(), items.data());
+    // Wide shape from N = 432: rows swept in groups of two (fewer HBM reads, clocks stay at maximum); below that
+    // and for the narrow shape, column-major with look-ahead.  GSN_ITEM_ORDER=cols|rows and GSN_ITEM_GROUP=n are
+    // tuning hooks for tools/shape_sweep.sh.
+    const char* order_env = getenv("GSN_ITEM_ORDER");
+    const char* group_env = getenv("GSN_ITEM_GROUP");
+    const bool rows = order_env ? (order_env[0] == 'r') : (!p->narrow && N >= gsn::kRowOrderMinN);
+    const int group = group_env ? std::max(1, atoi(group_env)) : 2;
+    pd.n_items = rows ? gsn::make_item_order_rows(pd.nblk, first_col.data(), group, items.data())
+                      : gsn::make_item_order(pd.nblk, first_col.data(), items.data());
     GSN_CUDA_P(cudaMalloc(&p->d_items, sizeof(unsigned) * items.size()));
     GSN_CUDA_P(cudaMemcpy(p->d_items, items.data(), sizeof(unsigned) * pd.n_items, cudaMemcpyHostToDevice));
     pd.items = p->d_items;
@@ -257,7 +269,6 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
 
   // persistent grid: CTAs/SM limited by registers (launch bounds) and shared memory
   const bool has_aux = kernel_kind == GSN_K_GIBBS || kernel_kind == GSN_K_JJ;
-  p->narrow = N <= gsn::kNarrowMaxN;    // one warp per theta while a theta has few work items (see CfgNarrow)
   p->smem_bytes = p->narrow ? gsn::logl_dmma_smem_bytes<gsn::CfgNarrow>(pd.Npad, has_aux) : gsn::logl_dmma_smem_bytes<gsn::CfgWide>(pd.Npad, has_aux);
   if (p->smem_bytes > 226 * 1024) return cleanup(fail(GSN_ERR_UNSUPPORTED, "N = %lld needs %zu bytes of shared memory", (long long)N, p->smem_bytes));
   const int cfg_ctas = p->narrow ? gsn::CfgNarrow::kCtasPerSm : gsn::CfgWide::kCtasPerSm;
