@@ -289,7 +289,8 @@ def run_own(args):
                              identical_to_device_path=same),
                     roofline=dict(bound="tensor", pipe="fp64 (DMMA.8x8x4, shared with DFMA)", achieved=achieved, peak=peak,
                                   unit="TFLOP/s", frac=achieved / peak, traffic=ncu_traffic(N, B), flops_per_eval=flops,
-                                  peak_source=peak_src, kernel="gsn::logl_dmma_kernel<0>", kernel_ms=kernel_ms),
+                                  peak_source=peak_src, kernel="gsn::logl_dmma_kernel<0, gsn::CfgWide>", kernel_ms=kernel_ms,
+                                  algorithmic_hbm_bytes_per_eval=int(theta_h.shape[1] * 8 + 8)),
                     nan_fraction=float(np.mean(~np.isfinite(out_h))))
         if world == 1 and not args.no_cpu:
             per_core = max(2, int(round(1.0 / (0.012 * (N / 512.0) ** 3))))
