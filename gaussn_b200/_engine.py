@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
     "gsn_problem_create", "gsn_problem_destroy", "gsn_problem_set_theta_map", "gsn_logl_batch",
     "gsn_logl_batch_host", "gsn_logl_batch_hostmean", "gsn_lens_batch", "gsn_query", "gsn_covariance",
     "gsn_mean", "gsn_lens", "gsn_kernel_nparams", "gsn_mean_nparams", "gsn_lens_nparams",
-    "gsn_abi_version", "gsn_last_error",
+    "gsn_abi_version", "gsn_last_error", "gsn_item_order",
 )
 
 
@@ -84,6 +84,8 @@ def load():
             getattr(lib, name).restype = C.c_int32
         lib.gsn_lens_nparams.argtypes = [C.c_int32, C.c_int32]
         lib.gsn_lens_nparams.restype = C.c_int32
+        lib.gsn_item_order.argtypes = [C.c_int64, _ip, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.c_int64]
+        lib.gsn_item_order.restype = C.c_int64
         _lib = lib
         return lib
 
@@ -137,6 +139,19 @@ def lens(kind: int, params, x, n_bands: int, n_images: int, indices, device=None
     _check(lib.gsn_lens(default_device() if device is None else device, kind, _ptr(p) if len(p) else None, len(p), _ptr(x),
                         len(x), n_bands, n_images, idx.ctypes.data_as(_lp), _ptr(xs), _ptr(b)))
     return xs, b
+
+
+def item_order(N: int, band_of_row=None, n_bands: int = 1, masked: bool = False):
+    """Work-item order of one evaluation as [(c, j, first_col), ...] (no GPU needed)."""
+    lib = load()
+    band = None if band_of_row is None else np.ascontiguousarray(np.asarray(band_of_row, dtype=np.int32))
+    bp = None if band is None else band.ctypes.data_as(_ip)
+    n = lib.gsn_item_order(N, bp, n_bands, int(masked), None, 0)
+    if n < 0:
+        raise GsnError(lib.gsn_last_error().decode())
+    out = np.empty(n, dtype=np.uint32)
+    lib.gsn_item_order(N, bp, n_bands, int(masked), out.ctypes.data_as(C.POINTER(C.c_uint32)), n)
+    return [(int((w >> 12) & 0xfff), int(w & 0xfff), int(w >> 24)) for w in out]
 
 
 # --- problem handle ---------------------------------------------------------

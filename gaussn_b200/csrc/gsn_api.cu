@@ -126,6 +126,44 @@ int check_indices(const int64_t* indices, int32_t n_bands, int32_t n_images, int
   return GSN_OK;
 }
 
+// Item list of one factorisation: band structure -> first non-zero block column per chunk -> order -> list scheduling.
+// `band_of_row` has N entries (band index per row, non-decreasing) or is null (one band).
+std::vector<unsigned> build_item_list(int64_t N, const int* band_of_row, int n_bands, bool masked, bool narrow) {
+  const int nblk = (int)((N + 31) / 32);
+  std::vector<int> lo(nblk), hi(nblk), first_col(nblk, 0);
+  for (int c = 0; c < nblk; ++c) {
+    const int64_t r0 = 32 * (int64_t)c, r1 = r0 + 31;
+    lo[c] = r0 < N ? (band_of_row ? band_of_row[r0] : 0) : n_bands;   // padding rows count as a band of their own
+    hi[c] = r1 < N ? (band_of_row ? band_of_row[r1] : 0) : n_bands;
+  }
+  if (masked)
+    for (int c = 0; c < nblk; ++c) {
+      int kb = 0;
+      while (kb < c && hi[kb] < lo[c]) ++kb;
+      first_col[c] = kb;
+    }
+  std::vector<unsigned> items((size_t)nblk * (nblk + 1) / 2);
+  // Wide shape from N = 432: rows swept in groups of two (fewer HBM reads, clocks stay at maximum); below that
+  // and for the narrow shape, column-major with look-ahead.  GSN_ITEM_ORDER=cols|rows and GSN_ITEM_GROUP=n are
+  // tuning hooks for tools/shape_sweep.sh.  (Re-ordering the list by a simulated greedy schedule, so that no item
+  // sits right behind its predecessor, was tried and lost 7 %: it breaks up the sweep that keeps HBM reads low.)
+  const char* order_env = getenv("GSN_ITEM_ORDER");
+  const char* group_env = getenv("GSN_ITEM_GROUP");
+  const bool rows = order_env ? (order_env[0] == 'r') : (!narrow && N >= gsn::kRowOrderMinN);
+  const int group = group_env ? std::max(1, atoi(group_env)) : 2;
+  const int n = rows ? gsn::make_item_order_rows(nblk, first_col.data(), group, items.data())
+                     : gsn::make_item_order(nblk, first_col.data(), items.data());
+  items.resize(n);
+  return items;
+}
+
+bool pick_narrow(int64_t N) {
+  // one warp per theta while a theta has few work items (see CfgNarrow); GSN_FORCE_SHAPE=narrow|wide is a tuning hook
+  bool narrow = N <= gsn::kNarrowDispatchN;
+  if (const char* shape_env = getenv("GSN_FORCE_SHAPE")) narrow = (shape_env[0] == 'n') && N <= gsn::kNarrowMaxN;
+  return narrow;
+}
+
 // scratch RAII for the single-call helpers
 struct DevBuf {
   void* p = nullptr;
@@ -197,9 +235,7 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   pd.nlog2pi = (double)N * std::log(2.0 * M_PI);
   p->n_theta_cols = pd.P;
 
-  // one warp per theta while a theta has few work items (see CfgNarrow); GSN_FORCE_SHAPE=narrow|wide is a tuning hook
-  p->narrow = N <= gsn::kNarrowDispatchN;
-  if (const char* shape_env = getenv("GSN_FORCE_SHAPE")) p->narrow = (shape_env[0] == 'n') && N <= gsn::kNarrowMaxN;
+  p->narrow = pick_narrow(N);
   // per-epoch tables (padded)
   std::vector<double> hx(pd.Npad, 0.0), hy(pd.Npad, 0.0), he(pd.Npad, 1.0);
   std::vector<int> himg(pd.Npad, 0), hband(pd.Npad, -1);
@@ -228,31 +264,9 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   GSN_CUDA_P(cudaMalloc(&p->d_theta_col, sizeof(int) * hcol.size()));
   GSN_CUDA_P(cudaMalloc(&p->d_theta_fixed, sizeof(double) * hfix.size()));
   GSN_CUDA_P(cudaMalloc(&p->d_counter, sizeof(unsigned)));
+  std::vector<unsigned> items = build_item_list(N, hband.data(), n_bands, pd.use_mask && n_bands > 1, p->narrow);
+  pd.n_items = (int)items.size();
   {
-    // band range of every 32-row chunk (padding rows count as a band of their own) -> first non-zero block column
-    const bool masked = pd.use_mask && n_bands > 1;
-    std::vector<int> lo(pd.nblk), hi(pd.nblk), first_col(pd.nblk, 0);
-    for (int c = 0; c < pd.nblk; ++c) {
-      const int r0 = 32 * c, r1 = 32 * c + 31;
-      lo[c] = r0 < N ? hband[r0] : n_bands;
-      hi[c] = r1 < N ? hband[r1] : n_bands;
-    }
-    if (masked)
-      for (int c = 0; c < pd.nblk; ++c) {
-        int kb = 0;
-        while (kb < c && hi[kb] < lo[c]) ++kb;
-        first_col[c] = kb;
-      }
-    std::vector<unsigned> items((size_t)pd.nblk * (pd.nblk + 1) / 2);
-    // Wide shape from N = 432: rows swept in groups of two (fewer HBM reads, clocks stay at maximum); below that
-    // and for the narrow shape, column-major with look-ahead.  GSN_ITEM_ORDER=cols|rows and GSN_ITEM_GROUP=n are
-    // tuning hooks for tools/shape_sweep.sh.
-    const char* order_env = getenv("GSN_ITEM_ORDER");
-    const char* group_env = getenv("GSN_ITEM_GROUP");
-    const bool rows = order_env ? (order_env[0] == 'r') : (!p->narrow && N >= gsn::kRowOrderMinN);
-    const int group = group_env ? std::max(1, atoi(group_env)) : 2;
-    pd.n_items = rows ? gsn::make_item_order_rows(pd.nblk, first_col.data(), group, items.data())
-                      : gsn::make_item_order(pd.nblk, first_col.data(), items.data());
     GSN_CUDA_P(cudaMalloc(&p->d_items, sizeof(unsigned) * items.size()));
     GSN_CUDA_P(cudaMemcpy(p->d_items, items.data(), sizeof(unsigned) * pd.n_items, cudaMemcpyHostToDevice));
     pd.items = p->d_items;
@@ -396,6 +410,13 @@ int gsn_logl_batch_host(gsn_problem* p, const double* theta_host, int64_t B, int
   std::memcpy(logl_host, p->h_logl, sizeof(double) * B);
   if (info_host) std::memcpy(info_host, p->h_info, sizeof(int) * B);
   return GSN_OK;
+}
+
+int64_t gsn_item_order(int64_t N, const int32_t* band_of_row, int32_t n_bands, int32_t masked, uint32_t* out, int64_t cap) {
+  if (N < 1 || N > 32 * (gsn::kMaxChunks - 1) || n_bands < 1) { fail(GSN_ERR_INVALID, "bad N or n_bands"); return -1; }
+  const std::vector<unsigned> items = build_item_list(N, band_of_row, n_bands, masked != 0 && n_bands > 1, pick_narrow(N));
+  if (out) for (int64_t i = 0; i < (int64_t)items.size() && i < cap; ++i) out[i] = items[i];
+  return (int64_t)items.size();
 }
 
 int64_t gsn_query(const gsn_problem* p, int32_t what) {

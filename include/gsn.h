@@ -168,6 +168,13 @@ int gsn_lens_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_t l
 
 int64_t gsn_query(const gsn_problem* p, int32_t what);
 
+/* Introspection, no device needed: the order in which the work items (32x32 blocks (c, j), c >= j, of the blocked
+ * Cholesky) of one evaluation are handed to warps, as built by gsn_problem_create for a data set of N rows whose
+ * band index per row is band_of_row (NULL = one band).  Item word: (first_col << 24) | (c << 12) | j.  Returns the
+ * number of items (also when out is NULL or cap is too small), -1 on bad arguments.  Blocks that the band mask
+ * (lensingmodels.py:39-51) makes identically zero are not listed. */
+int64_t gsn_item_order(int64_t N, const int32_t* band_of_row, int32_t n_bands, int32_t masked, uint32_t* out, int64_t cap);
+
 /* ---- single-call plugin evaluations (HOST pointers, synchronous) ------------ */
 
 /* kernel.covariance(x, x_prime, params): gaussn/kernels.py (each class's

@@ -135,3 +135,50 @@ def test_bench_flop_model():
         assert np.all(np.diff(seg) >= 0)
     th = benchdata.make_theta(100, 3)
     assert th.shape == (100, 7) and th[:, 1].min() >= 10 and th[:, 1].max() <= 40
+
+
+def _check_item_order(N, band_of_row, n_bands, masked):
+    """Every non-zero block exactly once, and every item after everything it waits for (the kernel's
+    warps pull items in this order and spin on unfinished predecessors: a non-topological list could deadlock)."""
+    from gaussn_b200 import _engine
+    items = _engine.item_order(N, band_of_row, n_bands, masked)
+    nblk = (N + 31) // 32
+    band = np.zeros(N, dtype=int) if band_of_row is None else np.asarray(band_of_row)
+    lo = [band[32 * c] if 32 * c < N else n_bands for c in range(nblk)]
+    hi = [band[32 * c + 31] if 32 * c + 31 < N else n_bands for c in range(nblk)]
+    first = [0] * nblk
+    if masked and n_bands > 1:
+        for c in range(nblk):
+            kb = 0
+            while kb < c and hi[kb] < lo[c]:
+                kb += 1
+            first[c] = kb
+    want = {(c, j) for c in range(nblk) for j in range(first[c], c + 1)}
+    got = [(c, j) for c, j, _ in items]
+    assert len(got) == len(set(got)) and set(got) == want
+    assert all(k0 == first[c] for c, j, k0 in items)
+    pos = {cj: i for i, cj in enumerate(got)}
+    for (c, j), i in pos.items():
+        deps = []
+        if j > first[c]:
+            deps += [(c, j - 1), (j, j - 1)] if c != j else [(j, j - 1)]
+        if c != j:
+            deps.append((j, j))
+        assert all(pos[d] < i for d in deps), ((c, j), deps)
+    return items
+
+
+@pytest.mark.parametrize("N", [1, 31, 32, 33, 64, 200, 352, 353, 432, 512, 1000, 2048, 4192])
+def test_item_order_is_complete_and_topological(libgsn, N):
+    _check_item_order(N, None, 1, False)
+
+
+def test_item_order_skips_zero_blocks_of_the_band_mask(libgsn):
+    for N, sizes in ((512, [128] * 4), (512, [256, 256]), (396, [132] * 3), (194, [51, 48, 45, 50]), (700, [100, 300, 300])):
+        band = np.repeat(np.arange(len(sizes)), sizes)
+        dense = _check_item_order(N, band, len(sizes), False)
+        masked = _check_item_order(N, band, len(sizes), True)
+        assert len(masked) < len(dense)
+    # without a mask (NoLensing) the bands stay coupled: nothing is skipped
+    nblk = 16
+    assert len(_check_item_order(512, np.repeat([0, 1], 256), 2, False)) == nblk * (nblk + 1) // 2
