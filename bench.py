@@ -226,11 +226,26 @@ def run_own(args):
     prob = gp._problem
     theta_d = torch.as_tensor(theta_h, device=dev)
     logl_d = torch.empty(B, dtype=torch.float64, device=dev)
-    gathered = torch.empty(B * world, dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
+    fused, gathered, collective = None, None, "none (single GPU)"
+    if world > 1:
+        # NVLink-native gather: the kernel stores each logL into every rank's gathered buffer (peer-mapped symmetric
+        # memory), followed by a barrier; falls back to an NCCL all-gather if symmetric memory cannot be set up here
+        try:
+            if args.gather == "nccl":
+                raise RuntimeError("NCCL all-gather requested")
+            from gaussn_b200 import sharding
+            fused = sharding.FusedGather(B, dev)
+            collective = "fused into the kernel epilogue: peer stores over NVLink into symmetric memory + barrier"
+        except Exception as exc:  # noqa: BLE001
+            gathered = torch.empty(B * world, dtype=torch.float64, device=dev)
+            collective = f"NCCL all_gather_into_tensor of {B} doubles per rank ({type(exc).__name__}: {exc})"
 
     def step():
+        if fused is not None:
+            fused.run(prob, theta_d)
+            return
         prob.logl_device(theta_d.data_ptr(), B, theta_d.shape[1], logl_d.data_ptr(), 0, 0, stream.cuda_stream)
         if world > 1:
             dist.all_gather_into_tensor(gathered, logl_d)
@@ -275,7 +290,8 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = B * world * args.steps / e2e_s
-    same = bool(np.array_equal(out_h, logl_d.cpu().numpy(), equal_nan=True))
+    dev_vals = (fused.buf[rank * B:(rank + 1) * B] if fused is not None else logl_d).cpu().numpy()
+    same = bool(np.array_equal(out_h, dev_vals, equal_nan=True))
 
     if rank == 0:
         flops = benchdata.algorithmic_flops(N, 1, True, KERNEL)
@@ -284,7 +300,8 @@ def run_own(args):
         achieved = flops * B / (kernel_ms * 1e-3) / 1e12
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                    data="synthetic", config=_config(args), clocks=clocks.summary(), gpu_launches=int(launches),
+                    data="synthetic", config=dict(_config(args), collective=collective), clocks=clocks.summary(),
+                    gpu_launches=int(launches),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(theta_h.nbytes), d2h_bytes_per_step=int(B * 12),
                              identical_to_device_path=same),
                     roofline=dict(bound="tensor", pipe="fp64 (DMMA.8x8x4, shared with DFMA)", achieved=achieved, peak=peak,
@@ -314,6 +331,7 @@ def main():
     ap.add_argument("--epochs", type=int, default=512)
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="multi-GPU result gather (default: fused peer stores)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

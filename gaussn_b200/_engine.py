@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
     "gsn_problem_create", "gsn_problem_destroy", "gsn_problem_set_theta_map", "gsn_logl_batch",
     "gsn_logl_batch_host", "gsn_logl_batch_hostmean", "gsn_lens_batch", "gsn_query", "gsn_covariance",
     "gsn_mean", "gsn_lens", "gsn_kernel_nparams", "gsn_mean_nparams", "gsn_lens_nparams",
-    "gsn_abi_version", "gsn_last_error", "gsn_item_order",
+    "gsn_abi_version", "gsn_last_error", "gsn_item_order", "gsn_logl_batch_gather",
 )
 
 
@@ -70,6 +70,8 @@ def load():
         lib.gsn_problem_destroy.argtypes = [C.c_void_p]
         lib.gsn_problem_set_theta_map.argtypes = [C.c_void_p, _ip, _dp]
         lib.gsn_logl_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.gsn_logl_batch_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_void_p), C.c_int32, C.c_int64,
+                                              C.c_void_p, C.c_uint32, C.c_void_p]
         lib.gsn_logl_batch_host.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, _dp, _ip, C.c_uint32]
         lib.gsn_logl_batch_hostmean.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_uint32, C.c_void_p]
@@ -222,6 +224,13 @@ class Problem:
     def logl_device(self, theta_ptr: int, B: int, ld: int, logl_ptr: int, info_ptr: int = 0, flags: int = 0, stream: int = 0):
         _check(self._lib.gsn_logl_batch(self._h, C.c_void_p(theta_ptr), B, ld, C.c_void_p(logl_ptr),
                                         C.c_void_p(info_ptr) if info_ptr else None, flags, C.c_void_p(stream) if stream else None))
+
+    def logl_device_gather(self, theta_ptr: int, B: int, ld: int, out_ptrs, out_offset: int, info_ptr: int = 0, flags: int = 0,
+                           stream: int = 0):
+        """Results go to index out_offset + i of every buffer in `out_ptrs` (own and NVLink-peer device pointers)."""
+        arr = (C.c_void_p * len(out_ptrs))(*[C.c_void_p(int(p)) for p in out_ptrs])
+        _check(self._lib.gsn_logl_batch_gather(self._h, C.c_void_p(theta_ptr), B, ld, arr, len(out_ptrs), out_offset,
+                                               C.c_void_p(info_ptr) if info_ptr else None, flags, C.c_void_p(stream) if stream else None))
 
     def logl_device_hostmean(self, theta_ptr: int, B: int, ld: int, mean_ptr: int, logl_ptr: int, info_ptr: int = 0,
                              flags: int = 0, stream: int = 0):

@@ -72,10 +72,10 @@ struct gsn_problem {
 
 namespace {
 
-int dispatch_logl(gsn_problem* p, const double* theta, int64_t B, int64_t ld, const double* hostmean,
-                  double* logl, int* info, unsigned flags, cudaStream_t stream) {
+int dispatch_logl_out(gsn_problem* p, const double* theta, int64_t B, int64_t ld, const double* hostmean,
+                      const gsn::GatherOut& out, int* info, unsigned flags, cudaStream_t stream) {
   GSN_CUDA(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned), stream));
-  gsn::LaunchArgs a{p->pd, theta, B, ld, hostmean, logl, info, flags, p->d_workspace, p->d_counter,
+  gsn::LaunchArgs a{p->pd, theta, B, ld, hostmean, out, info, flags, p->d_workspace, p->d_counter,
                     (int)std::min<int64_t>(B, p->grid), p->smem_bytes, stream};
   const int k = p->kernel_kind;
   cudaError_t e;
@@ -84,6 +84,13 @@ int dispatch_logl(gsn_problem* p, const double* theta, int64_t B, int64_t ld, co
   if (e != cudaSuccess) return fail(GSN_ERR_CUDA, "log-likelihood kernel launch failed: %s", cudaGetErrorString(e));
   p->launches += 1;
   return GSN_OK;
+}
+
+int dispatch_logl(gsn_problem* p, const double* theta, int64_t B, int64_t ld, const double* hostmean,
+                  double* logl, int* info, unsigned flags, cudaStream_t stream) {
+  gsn::GatherOut out{};
+  out.ptr[0] = logl; out.n = 1; out.offset = 0;
+  return dispatch_logl_out(p, theta, B, ld, hostmean, out, info, flags, stream);
 }
 
 template <int KIND>
@@ -353,6 +360,23 @@ int gsn_logl_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_t l
   if (B == 0) return GSN_OK;
   DeviceGuard guard(p->device);
   return dispatch_logl(p, theta_dev, B, ld, nullptr, logl_dev, info_dev, flags, (cudaStream_t)cuda_stream);
+}
+
+int gsn_logl_batch_gather(gsn_problem* p, const double* theta_dev, int64_t B, int64_t ld, double* const* out_ptrs,
+                          int32_t n_out, int64_t out_offset, int32_t* info_dev, uint32_t flags, void* cuda_stream) {
+  if (n_out < 1 || n_out > gsn::kMaxGather || !out_ptrs) return fail(GSN_ERR_INVALID, "n_out must be 1..%d and out_ptrs non-null", gsn::kMaxGather);
+  if (out_offset < 0) return fail(GSN_ERR_INVALID, "out_offset is negative");
+  gsn::GatherOut out{};
+  for (int r = 0; r < n_out; ++r) {
+    if (!out_ptrs[r]) return fail(GSN_ERR_INVALID, "out_ptrs[%d] is null", r);
+    out.ptr[r] = out_ptrs[r];
+  }
+  out.n = n_out; out.offset = out_offset;
+  if (int rc = check_batch_args(p, theta_dev, B, ld, out_ptrs[0])) return rc;
+  if (p->pd.mean_kind == GSN_M_HOST) return fail(GSN_ERR_INVALID, "problem uses a host-supplied mean: call gsn_logl_batch_hostmean");
+  if (B == 0) return GSN_OK;
+  DeviceGuard guard(p->device);
+  return dispatch_logl_out(p, theta_dev, B, ld, nullptr, out, info_dev, flags, (cudaStream_t)cuda_stream);
 }
 
 int gsn_logl_batch_hostmean(gsn_problem* p, const double* theta_dev, int64_t B, int64_t ld, const double* mean_dev,

@@ -18,7 +18,7 @@ static cudaError_t launch_one(const LaunchArgs& a) {
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
-  kern<<<a.grid, Cfg::kWarps * 32, a.smem_bytes, a.stream>>>(a.pd, a.theta, a.B, a.ld, a.hostmean, a.logl, a.info, a.flags,
+  kern<<<a.grid, Cfg::kWarps * 32, a.smem_bytes, a.stream>>>(a.pd, a.theta, a.B, a.ld, a.hostmean, a.out, a.info, a.flags,
                                                             a.workspace, a.counter);
   return cudaGetLastError();
 }

@@ -12,7 +12,7 @@ struct LaunchArgs {
   const double* theta;
   long long B, ld;
   const double* hostmean;
-  double* logl;
+  GatherOut out;
   int* info;
   unsigned flags;
   double* workspace;

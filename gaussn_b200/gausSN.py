@@ -243,12 +243,27 @@ class GP:
             raise ValueError(f"theta has {width} columns, expected {ncols} (kernel | mean | lensing minus fixed groups)")
         return self._evaluate(theta, _engine.FLAG_NEG_INF if neg_inf else 0)
 
-    def loglikelihood_batch_sharded(self, theta, group=None, **kwargs):
+    def loglikelihood_batch_sharded(self, theta, group=None, fused=False, **kwargs):
         """``loglikelihood_batch`` with the rows of ``theta`` split over the ranks of a
-        torch.distributed group (one process per GPU) and the results all-gathered; every
-        rank passes the same ``theta`` and receives the full vector."""
+        torch.distributed group (one process per GPU) and the results gathered; every
+        rank passes the same ``theta`` and receives the full vector.  ``fused=True`` (CUDA tensors
+        only) lets the kernel store each result directly into every rank's gathered buffer over
+        NVLink instead of issuing an all-gather afterwards."""
         from . import sharding
-        return sharding.evaluate_sharded(lambda th: self.loglikelihood_batch(th, **kwargs), theta, group)
+        if not fused:
+            return sharding.evaluate_sharded(lambda th: self.loglikelihood_batch(th, **kwargs), theta, group)
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        B = theta.shape[0]
+        start, stop, per = sharding.shard_bounds(B, world, rank)
+        self.loglikelihood_batch(theta[:0], **kwargs)          # programs the problem handle and the theta map
+        key = (per, theta.device, id(group))
+        if getattr(self, "_fused_key", None) != key:
+            self._fused = sharding.FusedGather(per, theta.device, group)
+            self._fused_key = key
+        flags = _engine.FLAG_NEG_INF if kwargs.get("neg_inf") else 0
+        out = self._fused.run(self._problem, theta[start:stop].contiguous(), flags)
+        return out[:B].clone() if per * world == B else out[:B].clone()
 
     def jointprobability(self, params, logprior=None, fix_kernel_params=False, fix_mean_params=False,
                          fix_lensing_params=False, invert=1):

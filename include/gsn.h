@@ -146,6 +146,15 @@ int gsn_problem_set_theta_map(gsn_problem* p, const int32_t* col_of_param, const
 int gsn_logl_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_t ld,
                    double* logl_dev, int32_t* info_dev, uint32_t flags, void* cuda_stream);
 
+/* gsn_logl_batch with the theta-sharded all-gather fused into the kernel: every result is stored at index
+ * out_offset + i of EACH of the n_out device buffers (this GPU's gathered buffer and the peer-mapped buffers of
+ * the other GPUs of the box, reachable over NVLink), so that after a cross-rank barrier every rank holds the
+ * logL of all shards without a separate collective.  out_ptrs is a host array of n_out (<= 16) device pointers.
+ * Replaces the (absent) multi-device story of the reference; see gaussn_b200/sharding.py. */
+int gsn_logl_batch_gather(gsn_problem* p, const double* theta_dev, int64_t B, int64_t ld,
+                          double* const* out_ptrs, int32_t n_out, int64_t out_offset,
+                          int32_t* info_dev, uint32_t flags, void* cuda_stream);
+
 /* The same call with HOST buffers: pinned staging, H2D of theta and D2H of the
  * results inside, synchronous.  This is the end-to-end path bench.py times. */
 int gsn_logl_batch_host(gsn_problem* p, const double* theta_host, int64_t B, int64_t ld,

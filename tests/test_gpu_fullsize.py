@@ -124,9 +124,13 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
 ds = benchdata.make_dataset(256, 1, 2); theta = benchdata.make_theta(1001, 2)
 gp = gausSN.GP(kernels.ExpSquaredKernel([0.3, 25.0]), meanfuncs.UniformMean([0.0]), lensingmodels.ConstantMagnification([20.0, 0.5]), device=rank)
 gp.x, gp.y, gp.yerr = ds["x"], ds["y"], ds["yerr"]; gp._prepare_indices(ds["x"], ds["band"], ds["image"])
-full = gp.loglikelihood_batch_sharded(torch.as_tensor(theta, device="cuda")).cpu().numpy()
+th_d = torch.as_tensor(theta, device="cuda")
+full = gp.loglikelihood_batch_sharded(th_d).cpu().numpy()
 single = gp.loglikelihood_batch(theta)
 assert np.array_equal(full, single), np.abs(full - single).max()
+for _ in range(3):   # NVLink-native path: the kernel stores into every rank's gathered buffer, then a barrier
+    fused = gp.loglikelihood_batch_sharded(th_d, fused=True).cpu().numpy()
+    assert np.array_equal(fused, single), np.abs(fused - single).max()
 dist.destroy_process_group(); print("rank", rank, "ok")
 ''')
     env = dict(os.environ, GSN_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
