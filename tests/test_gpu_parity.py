@@ -360,3 +360,27 @@ def test_minimize_with_batched_gradient(libgsn, golden):
                                  minimize_kwargs=dict(method="L-BFGS-B", batched_gradient=True,
                                                       bounds=[(0.01, 1.0), (10.0, 40.0), (30.0, 50.0), (0.1, 1.0)]))
     assert -res.fun >= 368.647, res       # the notebook's loglstar for this fit (ipynb/fitting_SLSN_example.ipynb:153)
+
+
+def test_hypothesis_random_layouts_and_theta(libgsn):
+    """Property sweep: random segment layouts, sizes and parameter points, random plugin triple."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    kernels_ok = ["ExpSquaredKernel", "ExponentialKernel", "Matern32Kernel", "Matern52Kernel", "OUKernel", "PeriodicKernel", "GibbsKernel"]
+    means_ok = ["UniformMean", "Sin", "Gaussian", "ExpFunction", "Bazin2009", "Karpenka2012", "Villar2019"]
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(seed=st.integers(0, 2**31 - 1), n_bands=st.integers(1, 4), n_images=st.integers(1, 4), per_seg=st.integers(1, 40),
+           kernel=st.sampled_from(kernels_ok), mean=st.sampled_from(means_ok), lens=st.sampled_from(["ConstantMagnification", "SigmoidMagnification", "NoLensing"]))
+    def run(seed, n_bands, n_images, per_seg, kernel, mean, lens):
+        rng = np.random.default_rng(seed)
+        if lens == "NoLensing":
+            n_images = 1
+        N = n_bands * n_images * per_seg + int(rng.integers(0, 5))
+        ds = _synth(rng, N, n_bands, n_images)
+        theta = _theta_box(rng, 6, kernel, mean, lens, n_images)
+        gp = _gp_for(ds, kernel, mean, lens, n_images, theta[0])
+        want = _oracle_batch(ds, theta, kernel, mean, lens, gp)
+        assert_logl_close(gp.loglikelihood_batch(theta), want, f"{kernel}/{mean}/{lens} N={N} bands={n_bands} images={n_images} seed={seed}")
+
+    run()
