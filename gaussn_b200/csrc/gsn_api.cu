@@ -60,7 +60,11 @@ struct gsn_problem {
   int* d_theta_col = nullptr; double* d_theta_fixed = nullptr; unsigned* d_items = nullptr;
   double* d_workspace = nullptr; size_t slot_doubles = 0; size_t workspace_bytes = 0;
   unsigned* d_counter = nullptr;
-  int grid = 0; size_t smem_bytes = 0; bool narrow = false;
+  // two launch shapes (see CfgWide / CfgNarrow): the narrow one is available for N <= kNarrowDispatchN and is
+  // chosen per call when the batch is large enough to fill the GPU with one-warp CTAs
+  bool narrow_ok = false;
+  int grid_wide = 0, grid_narrow = 0; size_t smem_wide = 0, smem_narrow = 0;
+  int last_shape = 0;
   int n_theta_cols = 0;   // columns the caller's theta must provide
   // host staging for gsn_logl_batch_host
   double* h_theta = nullptr; double* h_logl = nullptr; int* h_info = nullptr;
@@ -75,11 +79,16 @@ namespace {
 int dispatch_logl_out(gsn_problem* p, const double* theta, int64_t B, int64_t ld, const double* hostmean,
                       const gsn::GatherOut& out, int* info, unsigned flags, cudaStream_t stream) {
   GSN_CUDA(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned), stream));
+  // One warp per theta pays off once there are enough thetas to fill the GPU with such CTAs; for small batches
+  // (and single calls, which is how the reference's samplers use the likelihood) four warps per theta give the
+  // lower latency (N = 141: 96 us against 161 us per call; B = 4096: 1.04 ms against 1.33 ms the other way round).
+  const bool narrow = p->narrow_ok && B >= gsn::kNarrowMinBatch;
+  p->last_shape = narrow ? GSN_PATH_DMMA_BLOCKED_NARROW : GSN_PATH_DMMA_BLOCKED;
   gsn::LaunchArgs a{p->pd, theta, B, ld, hostmean, out, info, flags, p->d_workspace, p->d_counter,
-                    (int)std::min<int64_t>(B, p->grid), p->smem_bytes, stream};
+                    (int)std::min<int64_t>(B, narrow ? p->grid_narrow : p->grid_wide), narrow ? p->smem_narrow : p->smem_wide, stream};
   const int k = p->kernel_kind;
   cudaError_t e;
-  if (p->narrow) e = (k <= 4) ? gsn::launch_logl_narrow_a(k, a) : gsn::launch_logl_narrow_b(k, a);
+  if (narrow) e = (k <= 4) ? gsn::launch_logl_narrow_a(k, a) : gsn::launch_logl_narrow_b(k, a);
   else           e = (k <= 4) ? gsn::launch_logl_wide_a(k, a) : gsn::launch_logl_wide_b(k, a);
   if (e != cudaSuccess) return fail(GSN_ERR_CUDA, "log-likelihood kernel launch failed: %s", cudaGetErrorString(e));
   p->launches += 1;
@@ -242,7 +251,7 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   pd.nlog2pi = (double)N * std::log(2.0 * M_PI);
   p->n_theta_cols = pd.P;
 
-  p->narrow = pick_narrow(N);
+  p->narrow_ok = pick_narrow(N);
   // per-epoch tables (padded)
   std::vector<double> hx(pd.Npad, 0.0), hy(pd.Npad, 0.0), he(pd.Npad, 1.0);
   std::vector<int> himg(pd.Npad, 0), hband(pd.Npad, -1);
@@ -271,7 +280,7 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   GSN_CUDA_P(cudaMalloc(&p->d_theta_col, sizeof(int) * hcol.size()));
   GSN_CUDA_P(cudaMalloc(&p->d_theta_fixed, sizeof(double) * hfix.size()));
   GSN_CUDA_P(cudaMalloc(&p->d_counter, sizeof(unsigned)));
-  std::vector<unsigned> items = build_item_list(N, hband.data(), n_bands, pd.use_mask && n_bands > 1, p->narrow);
+  std::vector<unsigned> items = build_item_list(N, hband.data(), n_bands, pd.use_mask && n_bands > 1, p->narrow_ok);
   pd.n_items = (int)items.size();
   {
     GSN_CUDA_P(cudaMalloc(&p->d_items, sizeof(unsigned) * items.size()));
@@ -288,20 +297,20 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   pd.x = p->d_x; pd.y = p->d_y; pd.yerr2 = p->d_yerr2; pd.img = p->d_img; pd.band = p->d_band;
   pd.theta_col = p->d_theta_col; pd.theta_fixed = p->d_theta_fixed;
 
-  // persistent grid: CTAs/SM limited by registers (launch bounds) and shared memory
+  // persistent grids: CTAs/SM limited by registers (launch bounds) and shared memory, for both launch shapes
   const bool has_aux = kernel_kind == GSN_K_GIBBS || kernel_kind == GSN_K_JJ;
-  p->smem_bytes = p->narrow ? gsn::logl_dmma_smem_bytes<gsn::CfgNarrow>(pd.Npad, has_aux) : gsn::logl_dmma_smem_bytes<gsn::CfgWide>(pd.Npad, has_aux);
-  if (p->smem_bytes > 226 * 1024) return cleanup(fail(GSN_ERR_UNSUPPORTED, "N = %lld needs %zu bytes of shared memory", (long long)N, p->smem_bytes));
-  const int cfg_ctas = p->narrow ? gsn::CfgNarrow::kCtasPerSm : gsn::CfgWide::kCtasPerSm;
-  int per_sm = (int)std::min<size_t>(cfg_ctas, (size_t)(227 * 1024) / (p->smem_bytes + 1024));
-  per_sm = std::max(per_sm, 1);
+  p->smem_wide = gsn::logl_dmma_smem_bytes<gsn::CfgWide>(pd.Npad, has_aux);
+  p->smem_narrow = gsn::logl_dmma_smem_bytes<gsn::CfgNarrow>(pd.Npad, has_aux);
+  if (p->smem_wide > 226 * 1024) return cleanup(fail(GSN_ERR_UNSUPPORTED, "N = %lld needs %zu bytes of shared memory", (long long)N, p->smem_wide));
+  auto ctas_per_sm = [](int cfg_ctas, size_t smem) { return std::max(1, (int)std::min<size_t>(cfg_ctas, (size_t)(227 * 1024) / (smem + 1024))); };
   p->slot_doubles = gsn::logl_dmma_slot_doubles(pd.Npad);
-  // bound the workspace to a quarter of device memory for very large N
+  // bound the workspace to half of the free device memory for very large N
   size_t free_b = 0, total_b = 0;
   GSN_CUDA_P(cudaMemGetInfo(&free_b, &total_b));
-  size_t max_slots = std::max<size_t>(1, (free_b / 2) / (p->slot_doubles * sizeof(double)));
-  p->grid = (int)std::min<size_t>((size_t)p->sm_count * per_sm, max_slots);
-  p->workspace_bytes = (size_t)p->grid * p->slot_doubles * sizeof(double);
+  const size_t max_slots = std::max<size_t>(1, (free_b / 2) / (p->slot_doubles * sizeof(double)));
+  p->grid_wide = (int)std::min<size_t>((size_t)p->sm_count * ctas_per_sm(gsn::CfgWide::kCtasPerSm, p->smem_wide), max_slots);
+  p->grid_narrow = p->narrow_ok ? (int)std::min<size_t>((size_t)p->sm_count * ctas_per_sm(gsn::CfgNarrow::kCtasPerSm, p->smem_narrow), max_slots) : 0;
+  p->workspace_bytes = (size_t)std::max(p->grid_wide, p->grid_narrow) * p->slot_doubles * sizeof(double);
   GSN_CUDA_P(cudaMalloc(&p->d_workspace, p->workspace_bytes));
   GSN_CUDA_P(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
 #undef GSN_CUDA_P
@@ -452,11 +461,11 @@ int64_t gsn_query(const gsn_problem* p, int32_t what) {
     case GSN_Q_NPARAMS_MEAN: return p->pd.nm;
     case GSN_Q_NPARAMS_LENS: return p->pd.nl;
     case GSN_Q_WORKSPACE_BYTES: return (int64_t)p->workspace_bytes;
-    case GSN_Q_GRID: return p->grid;
+    case GSN_Q_GRID: return std::max(p->grid_wide, p->grid_narrow);
     case GSN_Q_DEVICE: return p->device;
     case GSN_Q_LAUNCHES: return p->launches;
     case GSN_Q_NPAD: return p->pd.Npad;
-    case GSN_Q_PATH: return p->narrow ? GSN_PATH_DMMA_BLOCKED_NARROW : GSN_PATH_DMMA_BLOCKED;
+    case GSN_Q_PATH: return p->last_shape;   // shape of the most recent launch (0 before the first)
   }
   return -1;
 }

@@ -95,12 +95,12 @@ typedef enum gsn_query_what {
   GSN_Q_DEVICE = 7,
   GSN_Q_LAUNCHES = 8,        /* kernels launched through this handle so far */
   GSN_Q_NPAD = 9,            /* padded matrix order used on the device */
-  GSN_Q_PATH = 10            /* which device path the handle dispatches to (gsn_path) */
+  GSN_Q_PATH = 10            /* launch shape of the handle's most recent batch call (gsn_path; 0 before the first) */
 } gsn_query_what;
 
 typedef enum gsn_path {
-  GSN_PATH_DMMA_BLOCKED = 1,        /* four warps per theta (N > 352): blocked left-looking Cholesky, FP64 DMMA updates, L in a global workspace */
-  GSN_PATH_DMMA_BLOCKED_NARROW = 2  /* the same kernel, one warp per theta (N <= 352) */
+  GSN_PATH_DMMA_BLOCKED = 1,        /* four warps per theta (N > 352, or batches below 512 thetas): blocked left-looking Cholesky, FP64 DMMA updates, L in a global workspace */
+  GSN_PATH_DMMA_BLOCKED_NARROW = 2  /* the same kernel, one warp per theta (N <= 352 and B >= 512) */
 } gsn_path;
 
 /*
