@@ -23,9 +23,10 @@ struct LaunchArgs {
 };
 
 // Each returns cudaSuccess, a CUDA error, or cudaErrorInvalidValue if `kind` is not in its slice.
-cudaError_t launch_logl_wide_a(int kind, const LaunchArgs& a);     // kinds 0..4
-cudaError_t launch_logl_wide_b(int kind, const LaunchArgs& a);     // kinds 5..10
-cudaError_t launch_logl_narrow_a(int kind, const LaunchArgs& a);
-cudaError_t launch_logl_narrow_b(int kind, const LaunchArgs& a);
+// a == nullptr only prepares the kernel (shared-memory attribute, image load) on the current device.
+cudaError_t launch_logl_wide_a(int kind, const LaunchArgs* a);     // kinds 0..4
+cudaError_t launch_logl_wide_b(int kind, const LaunchArgs* a);     // kinds 5..10
+cudaError_t launch_logl_narrow_a(int kind, const LaunchArgs* a);
+cudaError_t launch_logl_narrow_b(int kind, const LaunchArgs* a);
 
 }  // namespace gsn
