@@ -263,7 +263,7 @@ class GP:
             self._fused_key = key
         flags = _engine.FLAG_NEG_INF if kwargs.get("neg_inf") else 0
         out = self._fused.run(self._problem, theta[start:stop].contiguous(), flags)
-        return out[:B].clone() if per * world == B else out[:B].clone()
+        return out[:B].clone()    # gathered index rank * per + i is the global row index, also for a ragged last shard
 
     def jointprobability(self, params, logprior=None, fix_kernel_params=False, fix_mean_params=False,
                          fix_lensing_params=False, invert=1):
