@@ -384,3 +384,23 @@ def test_hypothesis_random_layouts_and_theta(libgsn):
         assert_logl_close(gp.loglikelihood_batch(theta), want, f"{kernel}/{mean}/{lens} N={N} bands={n_bands} images={n_images} seed={seed}")
 
     run()
+
+
+@pytest.mark.parametrize("kernel,n_bands,n_images,N", [("ExpSquaredKernel", 1, 2, 141), ("Matern32Kernel", 4, 2, 194), ("OUKernel", 1, 3, 33),
+                                                       ("GibbsKernel", 2, 2, 200), ("JJKernel", 1, 2, 96), ("Matern52Kernel", 3, 2, 352)])
+def test_one_warp_per_theta_shape_on_large_batches(libgsn, kernel, n_bands, n_images, N):
+    """Batches of 512+ theta at N <= 352 run the narrow launch shape (one warp per theta); smaller batches of the
+    same problem run the four-warp shape.  Both must agree with the oracle and with each other bit for bit."""
+    from gaussn_b200 import _engine
+    rng = np.random.default_rng(N * 7 + n_bands)
+    ds = _synth(rng, N, n_bands, n_images)
+    theta = _theta_box(rng, 640, kernel, "UniformMean", "ConstantMagnification", n_images)
+    theta[17, 0] = -abs(theta[17, 0])          # a non-PD point inside the batch
+    gp = _gp_for(ds, kernel, "UniformMean", "ConstantMagnification", n_images, theta[0])
+    big = gp.loglikelihood_batch(theta)
+    assert gp._problem.query(_engine.Q_PATH) == 2
+    small = np.concatenate([gp.loglikelihood_batch(theta[i:i + 160]) for i in range(0, 640, 160)])
+    assert gp._problem.query(_engine.Q_PATH) == 1
+    np.testing.assert_array_equal(big, small)
+    want = _oracle_batch(ds, theta[:96], kernel, "UniformMean", "ConstantMagnification", gp)
+    assert_logl_close(big[:96], want, f"narrow {kernel} N={N}")
