@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import _engine, lensingmodels
+from . import _engine, lensingmodels, samplers
 
 try:  # optional samplers, exactly as the reference treats them (gausSN.py:6-21)
     from scipy.optimize import minimize
@@ -349,9 +349,8 @@ class GP:
                 raise ImportError("dynesty is not installed")
             nlive = sampler_kwargs.pop('nlive', 500)
             sample = sampler_kwargs.pop('sample', 'rslice')
-            if isinstance(sampler_kwargs.get('pool'), __import__('gaussn_b200.samplers', fromlist=['BatchPool']).BatchPool):
+            if isinstance(sampler_kwargs.get('pool'), samplers.BatchPool):
                 # batched queue evaluation: the pool recognises this callable and evaluates whole queues at once
-                from . import samplers
                 post = samplers.VectorizedPosterior(self, *args)
                 sampler_kwargs.setdefault('queue_size', sampler_kwargs['pool'].size)
                 sampler = dynesty.NestedSampler(post, ptform, self.ndim, nlive=nlive, sample=sample, **sampler_kwargs)
@@ -373,7 +372,6 @@ class GP:
                     raise ImportError("scipy is not installed")
                 if minimize_kwargs.pop('batched_gradient', False):
                     # value and forward-difference gradient from one batch of P + 1 points per iteration
-                    from . import samplers
                     post = samplers.VectorizedPosterior(self, logprior, fix_kernel_params, fix_mean_params, fix_lensing_params, -1)
                     bounds = minimize_kwargs.get('bounds')
                     return minimize(lambda th: samplers.fd_value_and_grad(post, th, bounds=bounds), init_pos, jac=True, **minimize_kwargs)
@@ -390,7 +388,6 @@ class GP:
                 while np.isinf(logprior(row)):
                     p0[r] = row = np.random.normal(init_pos, 0.001)
             # both ensemble samplers accept vectorize=True: the whole half-ensemble is one GPU batch per step
-            from . import samplers
             post = samplers.VectorizedPosterior(self, *args)
             sampler_kwargs.setdefault('vectorize', True)
             logprob = post if sampler_kwargs['vectorize'] else self.jointprobability
