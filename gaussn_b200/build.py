@@ -25,6 +25,10 @@ SOURCES = [os.path.join(CSRC, "gsn_api.cu"), os.path.join(CSRC, "gsn_kernels.cu"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
+    # no implicit multiply-add contraction: every fused operation in the kernels is an explicit fma(), so the two
+    # launch shapes (separately compiled instantiations) produce bit-identical results, and the unfused plugin
+    # formulas round like the reference's numpy/XLA arithmetic
+    "-fmad=false",
     "-Xcompiler", "-fPIC",
 ]
 # translation units: the C ABI plus four slices of kernel instantiations ({shape} x {kinds}), built in parallel

@@ -5,7 +5,7 @@ set -e
 name=$1; shift
 root=$(cd "$(dirname "$0")/.." && pwd)
 T=$(mktemp -d); mkdir -p "$root/variants"
-F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $*"
+F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC $*"
 cd "$root/gaussn_b200/csrc"
 nvcc $F -c -o $T/api.o gsn_api.cu &
 nvcc $F -DGSN_SLICE_CFG=CfgWide -DGSN_SLICE_NAME=launch_logl_wide_a -DGSN_SLICE_LO=0 -DGSN_SLICE_HI=4 -c -o $T/wa.o gsn_kernels.cu &
