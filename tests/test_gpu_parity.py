@@ -404,3 +404,49 @@ def test_one_warp_per_theta_shape_on_large_batches(libgsn, kernel, n_bands, n_im
     np.testing.assert_array_equal(big, small)
     want = _oracle_batch(ds, theta[:96], kernel, "UniformMean", "ConstantMagnification", gp)
     assert_logl_close(big[:96], want, f"narrow {kernel} N={N}")
+
+
+def test_host_supplied_mean_with_fixed_groups(libgsn):
+    """The host-mean path under fix_* flags: fixed mean parameters come from the plugin, fixed kernel / lensing
+    parameters from the handle's theta map."""
+    from gaussn_b200 import gausSN, kernels, meanfuncs, lensingmodels
+
+    class FakeModel:
+        param_names = ["A", "beta", "t0", "Tfall", "Trise"]
+
+        def __init__(self):
+            self.parameters = np.array([1.0, 0.1, 30.0, 40.0, 8.0])
+
+        def update(self, d):
+            for k, v in d.items():
+                self.parameters[self.param_names.index(k)] = v
+
+        def bandflux(self, bands, t, zp=None, zpsys=None):
+            return gp_oracle.mean("Bazin2009", list(self.parameters), t)
+
+    rng = np.random.default_rng(21)
+    ds = _synth(rng, 70, 1, 2)
+    theta = _theta_box(rng, 9, "ExpSquaredKernel", "Bazin2009", "ConstantMagnification", 2)
+    k0, m0, l0 = [0.3, 8.0], [1.2, 0.05, 33.0, 41.0, 7.0], [5.0, 0.9]
+
+    def fresh():
+        gp = gausSN.GP(kernels.ExpSquaredKernel(list(k0)), meanfuncs.sncosmoMean(FakeModel()), lensingmodels.ConstantMagnification(list(l0)))
+        gp.meanfunc._reset(list(m0))
+        gp.x, gp.y, gp.yerr, gp.bands = ds["x"], ds["y"], ds["yerr"], ds["band"]
+        gp._prepare_indices(ds["x"], ds["band"], ds["image"])
+        return gp
+
+    def oracle(kp, mp, lp):
+        return gp_oracle.loglikelihood(ds["x"], ds["y"], ds["yerr"], "ExpSquaredKernel", kp, "Bazin2009", mp, "ConstantMagnification", lp,
+                                       1, 2, fresh().indices)
+
+    # kernel fixed: theta = mean | lensing
+    got = fresh().loglikelihood_batch(theta[:, 2:], fix_kernel_params=True)
+    assert_logl_close(got, [oracle(k0, list(t[2:7]), list(t[7:])) for t in theta], "host mean, kernel fixed")
+    # mean fixed: theta = kernel | lensing
+    th = np.column_stack([theta[:, :2], theta[:, 7:]])
+    got = fresh().loglikelihood_batch(th, fix_mean_params=True)
+    assert_logl_close(got, [oracle(list(t[:2]), m0, list(t[7:])) for t in theta], "host mean, mean fixed")
+    # lensing fixed: theta = kernel | mean
+    got = fresh().loglikelihood_batch(theta[:, :7], fix_lensing_params=True)
+    assert_logl_close(got, [oracle(list(t[:2]), list(t[2:7]), l0) for t in theta], "host mean, lensing fixed")
