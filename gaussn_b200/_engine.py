@@ -27,7 +27,9 @@ EXPORTED_SYMBOLS = (
     "gsn_logl_batch_host", "gsn_logl_batch_hostmean", "gsn_lens_batch", "gsn_query", "gsn_covariance",
     "gsn_mean", "gsn_lens", "gsn_kernel_nparams", "gsn_mean_nparams", "gsn_lens_nparams",
     "gsn_abi_version", "gsn_last_error", "gsn_item_order", "gsn_logl_batch_gather",
+    "gsn_predict_batch", "gsn_predict_batch_host",
 )
+MAX_ORDER = 4160   # largest padded order of a factorisation (32 * 130 block rows), also for n_rows + M of a prediction
 
 
 class GsnError(RuntimeError):
@@ -76,6 +78,10 @@ def load():
         lib.gsn_logl_batch_hostmean.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_uint32, C.c_void_p]
         lib.gsn_lens_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gsn_predict_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gsn_predict_batch_host.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _dp, C.c_int64,
+                                               _dp, _dp, _dp, _dp, _ip]
         lib.gsn_query.argtypes = [C.c_void_p, C.c_int32]
         lib.gsn_query.restype = C.c_int64
         lib.gsn_covariance.argtypes = [C.c_int, C.c_int32, _dp, C.c_int32, _dp, C.c_int64, _dp, C.c_int64, _dp]
@@ -241,3 +247,27 @@ class Problem:
     def lens_device(self, theta_ptr: int, B: int, ld: int, shifted_ptr: int, b_ptr: int, stream: int = 0):
         _check(self._lib.gsn_lens_batch(self._h, C.c_void_p(theta_ptr), B, ld, C.c_void_p(shifted_ptr), C.c_void_p(b_ptr),
                                         C.c_void_p(stream) if stream else None))
+
+    # GP.predict for a batch of theta: rows [row0, row0 + n_rows) are conditioned on, x_prime are the new epochs
+    def predict_host(self, theta, row0: int, n_rows: int, x_prime, mean_v=None, mean_u=None, want_cov: bool = True):
+        theta = _f64(theta)
+        if theta.ndim == 1:
+            theta = theta.reshape(1, -1)
+        B, ld = theta.shape
+        xp = _f64(x_prime).ravel()
+        M = len(xp)
+        mv = None if mean_v is None else _f64(mean_v).reshape(B, n_rows)
+        mu = None if mean_u is None else _f64(mean_u).reshape(B, M)
+        e = np.empty((B, M), dtype=np.float64)
+        v = np.empty((B, M, M), dtype=np.float64) if want_cov else None
+        info = np.empty(B, dtype=np.int32)
+        _check(self._lib.gsn_predict_batch_host(self._h, _ptr(theta) if theta.size else None, B, ld, row0, n_rows, _ptr(xp), M,
+                                                None if mv is None else _ptr(mv), None if mu is None else _ptr(mu), _ptr(e),
+                                                None if v is None else _ptr(v), info.ctypes.data_as(_ip)))
+        return e, v, info
+
+    def predict_device(self, theta_ptr: int, B: int, ld: int, row0: int, n_rows: int, xprime_ptr: int, M: int, exp_ptr: int,
+                       var_ptr: int = 0, info_ptr: int = 0, mean_v_ptr: int = 0, mean_u_ptr: int = 0, stream: int = 0):
+        vp = lambda q: C.c_void_p(q) if q else None
+        _check(self._lib.gsn_predict_batch(self._h, vp(theta_ptr), B, ld, row0, n_rows, vp(xprime_ptr), M, vp(mean_v_ptr),
+                                           vp(mean_u_ptr), vp(exp_ptr), vp(var_ptr), vp(info_ptr), vp(stream)))

@@ -19,9 +19,10 @@ HEADERS = [
     os.path.join(CSRC, "gsn_device.cuh"),
     os.path.join(CSRC, "gsn_chol_dmma.cuh"),
     os.path.join(CSRC, "gsn_launch.h"),
+    os.path.join(CSRC, "gsn_predict.cuh"),
     os.path.join(REPO_DIR, "include", "gsn.h"),
 ]
-SOURCES = [os.path.join(CSRC, "gsn_api.cu"), os.path.join(CSRC, "gsn_kernels.cu")]
+SOURCES = [os.path.join(CSRC, "gsn_api.cu"), os.path.join(CSRC, "gsn_kernels.cu"), os.path.join(CSRC, "gsn_predict.cu")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -31,13 +32,16 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-Xcompiler", "-fPIC",
 ]
-# translation units: the C ABI plus four slices of kernel instantiations ({shape} x {kinds}), built in parallel
+# translation units: the C ABI, four slices of likelihood-kernel instantiations ({shape} x {kinds}) and two of the
+# prediction kernel, built in parallel
 UNITS = [
     ("gsn_api", "gsn_api.cu", []),
     ("gsn_wide_a", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgWide", "-DGSN_SLICE_NAME=launch_logl_wide_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),
     ("gsn_wide_b", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgWide", "-DGSN_SLICE_NAME=launch_logl_wide_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
     ("gsn_narrow_a", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgNarrow", "-DGSN_SLICE_NAME=launch_logl_narrow_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),
     ("gsn_narrow_b", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgNarrow", "-DGSN_SLICE_NAME=launch_logl_narrow_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
+    ("gsn_predict_a", "gsn_predict.cu", ["-DGSN_SLICE_NAME=launch_predict_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),
+    ("gsn_predict_b", "gsn_predict.cu", ["-DGSN_SLICE_NAME=launch_predict_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
 ]
 
 

@@ -73,6 +73,11 @@ struct gsn_problem {
   int64_t stage_rows = 0; int64_t stage_ld = 0;
   cudaStream_t own_stream = nullptr;
   long long launches = 0;
+  // gsn_predict_batch: workspace and item list, sized on demand
+  double* d_pred_ws = nullptr; size_t pred_ws_bytes = 0;
+  unsigned* d_pred_items = nullptr; size_t pred_items_cap = 0; int pred_n_items = 0;
+  long long pred_key = -1;   // (n_rows padded, M, with covariance) of the item list held
+  bool pred_loaded = false;
 };
 
 namespace {
@@ -328,6 +333,7 @@ int gsn_problem_destroy(gsn_problem* p) {
   cudaFree(p->d_x); cudaFree(p->d_y); cudaFree(p->d_yerr2); cudaFree(p->d_img); cudaFree(p->d_band);
   cudaFree(p->d_theta_col); cudaFree(p->d_theta_fixed); cudaFree(p->d_workspace); cudaFree(p->d_counter); cudaFree(p->d_items);
   cudaFree(p->d_theta); cudaFree(p->d_logl); cudaFree(p->d_info);
+  cudaFree(p->d_pred_ws); cudaFree(p->d_pred_items);
   if (p->h_theta) cudaFreeHost(p->h_theta);
   if (p->h_logl) cudaFreeHost(p->h_logl);
   if (p->h_info) cudaFreeHost(p->h_info);
@@ -456,6 +462,100 @@ int gsn_logl_batch_host(gsn_problem* p, const double* theta_host, int64_t B, int
   GSN_CUDA(cudaStreamSynchronize(st));
   std::memcpy(logl_host, p->h_logl, sizeof(double) * B);
   if (info_host) std::memcpy(info_host, p->h_info, sizeof(int) * B);
+  return GSN_OK;
+}
+
+int gsn_predict_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_t ld, int64_t row0, int64_t n_rows,
+                      const double* xprime_dev, int64_t M, const double* mean_v_dev, const double* mean_u_dev,
+                      double* expectation_dev, double* variance_dev, int32_t* info_dev, void* cuda_stream) {
+  if (int rc = check_batch_args(p, theta_dev, B, ld, expectation_dev)) return rc;
+  if (row0 < 0 || n_rows < 1 || row0 + n_rows > p->pd.N) return fail(GSN_ERR_INVALID, "rows [%lld, %lld) are outside the problem's %d rows", (long long)row0, (long long)(row0 + n_rows), p->pd.N);
+  if (M < 1 || !xprime_dev) return fail(GSN_ERR_INVALID, "xprime_dev must be non-null, M >= 1");
+  const int64_t u0 = (n_rows + 31) / 32 * 32, Npad = (u0 + M + 31) / 32 * 32;
+  if (Npad / 32 > gsn::kMaxChunks - 1) return fail(GSN_ERR_UNSUPPORTED, "n_rows (padded to %lld) + M = %lld exceeds %d", (long long)u0, (long long)(u0 + M), 32 * (gsn::kMaxChunks - 1));
+  if (p->kernel_kind == GSN_K_JJ) return fail(GSN_ERR_UNSUPPORTED, "JJKernel.covariance(x', x) needs equal lengths (kernels.py:555): no prediction");
+  const bool host_mean = p->pd.mean_kind == GSN_M_HOST;
+  if (host_mean && B > 0 && (!mean_v_dev || !mean_u_dev)) return fail(GSN_ERR_INVALID, "problem uses a host-supplied mean: mean_v_dev and mean_u_dev are required");
+  if (!host_mean && (mean_v_dev || mean_u_dev)) return fail(GSN_ERR_INVALID, "mean_v_dev / mean_u_dev are only for GSN_M_HOST problems");
+  if (B == 0) return GSN_OK;
+  DeviceGuard guard(p->device);
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  const int k = p->kernel_kind;
+  if (!p->pred_loaded) {
+    GSN_CUDA((k <= 4) ? gsn::launch_predict_a(k, nullptr) : gsn::launch_predict_b(k, nullptr));
+    p->pred_loaded = true;
+  }
+  gsn::PredictDev pa{};
+  pa.row0 = (int)row0; pa.nV = (int)n_rows; pa.u0 = (int)u0; pa.nTot = (int)(u0 + M);
+  pa.Npad = (int)Npad; pa.nblk = (int)(Npad / 32); pa.nVb = (int)(u0 / 32); pa.M = (int)M;
+  pa.xprime = xprime_dev; pa.mean_v = mean_v_dev; pa.mean_u = mean_u_dev;
+  pa.expectation = expectation_dev; pa.variance = variance_dev;
+  // item list: cached per (padded rows, M, covariance wanted); replacing it waits for launches that may still read it
+  const long long key = ((long long)u0 << 32) | ((long long)M << 1) | (variance_dev ? 1 : 0);
+  if (key != p->pred_key) {
+    std::vector<unsigned> items((size_t)pa.nblk * (pa.nblk + 1) / 2);
+    const int n = gsn::make_item_order_predict(pa.nVb, pa.nblk, variance_dev != nullptr, items.data());
+    GSN_CUDA(cudaDeviceSynchronize());
+    if ((size_t)n > p->pred_items_cap) {
+      cudaFree(p->d_pred_items); p->d_pred_items = nullptr; p->pred_items_cap = 0;
+      GSN_CUDA(cudaMalloc(&p->d_pred_items, sizeof(unsigned) * n));
+      p->pred_items_cap = n;
+    }
+    GSN_CUDA(cudaMemcpy(p->d_pred_items, items.data(), sizeof(unsigned) * n, cudaMemcpyHostToDevice));
+    p->pred_n_items = n;
+    p->pred_key = key;
+  }
+  pa.items = p->d_pred_items; pa.n_items = p->pred_n_items;
+  const size_t smem = gsn::predict_smem_bytes(pa.Npad);
+  if (smem > 226 * 1024) return fail(GSN_ERR_UNSUPPORTED, "prediction of order %d needs %zu bytes of shared memory", pa.Npad, smem);
+  const int ctas = std::max(1, (int)std::min<size_t>(gsn::CfgWide::kCtasPerSm, (size_t)(227 * 1024) / (smem + 1024)));
+  const size_t slot_bytes = gsn::predict_slot_doubles(pa.Npad) * sizeof(double);
+  int grid = (int)std::min<int64_t>(B, (int64_t)p->sm_count * ctas);
+  if ((size_t)grid * slot_bytes > p->pred_ws_bytes) {
+    size_t free_b = 0, total_b = 0;
+    GSN_CUDA(cudaDeviceSynchronize());
+    cudaFree(p->d_pred_ws); p->d_pred_ws = nullptr; p->pred_ws_bytes = 0;
+    GSN_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    grid = (int)std::min<size_t>(grid, std::max<size_t>(1, (free_b / 2) / slot_bytes));
+    GSN_CUDA(cudaMalloc(&p->d_pred_ws, (size_t)grid * slot_bytes));
+    p->pred_ws_bytes = (size_t)grid * slot_bytes;
+  }
+  GSN_CUDA(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned), stream));
+  gsn::PredictLaunchArgs a{p->pd, pa, theta_dev, B, ld, info_dev, p->d_pred_ws, p->d_counter, grid, smem, stream};
+  const cudaError_t e = (k <= 4) ? gsn::launch_predict_a(k, &a) : gsn::launch_predict_b(k, &a);
+  if (e != cudaSuccess) return fail(GSN_ERR_CUDA, "prediction kernel launch failed: %s", cudaGetErrorString(e));
+  p->launches += 1;
+  return GSN_OK;
+}
+
+int gsn_predict_batch_host(gsn_problem* p, const double* theta_host, int64_t B, int64_t ld, int64_t row0, int64_t n_rows,
+                           const double* xprime_host, int64_t M, const double* mean_v_host, const double* mean_u_host,
+                           double* expectation_host, double* variance_host, int32_t* info_host) {
+  if (int rc = check_batch_args(p, theta_host, B, ld, expectation_host)) return rc;
+  if (M < 1 || !xprime_host) return fail(GSN_ERR_INVALID, "xprime_host must be non-null, M >= 1");
+  if (n_rows < 1) return fail(GSN_ERR_INVALID, "n_rows must be >= 1");
+  if (B == 0) return GSN_OK;
+  DeviceGuard guard(p->device);
+  DevBuf dth, dxp, dmv, dmu, dex, dvar, dinfo;
+  auto up = [&](DevBuf& b, const double* src, size_t n) -> cudaError_t {
+    cudaError_t e = b.alloc(sizeof(double) * n);
+    if (e == cudaSuccess && n) e = cudaMemcpy(b.p, src, sizeof(double) * n, cudaMemcpyHostToDevice);
+    return e;
+  };
+  GSN_CUDA(up(dth, theta_host, (size_t)B * ld));
+  GSN_CUDA(up(dxp, xprime_host, (size_t)M));
+  if (mean_v_host) GSN_CUDA(up(dmv, mean_v_host, (size_t)B * n_rows));
+  if (mean_u_host) GSN_CUDA(up(dmu, mean_u_host, (size_t)B * M));
+  GSN_CUDA(dex.alloc(sizeof(double) * B * M));
+  if (variance_host) GSN_CUDA(dvar.alloc(sizeof(double) * B * M * M));
+  GSN_CUDA(dinfo.alloc(sizeof(int) * B));
+  if (int rc = gsn_predict_batch(p, dth.as<double>(), B, ld, row0, n_rows, dxp.as<double>(), M,
+                                 mean_v_host ? dmv.as<double>() : nullptr, mean_u_host ? dmu.as<double>() : nullptr,
+                                 dex.as<double>(), variance_host ? dvar.as<double>() : nullptr, dinfo.as<int>(), p->own_stream)) return rc;
+  GSN_CUDA(cudaStreamSynchronize(p->own_stream));
+  GSN_CUDA(cudaMemcpy(expectation_host, dex.p, sizeof(double) * B * M, cudaMemcpyDeviceToHost));
+  if (variance_host) GSN_CUDA(cudaMemcpy(variance_host, dvar.p, sizeof(double) * B * M * M, cudaMemcpyDeviceToHost));
+  if (info_host) GSN_CUDA(cudaMemcpy(info_host, dinfo.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
   return GSN_OK;
 }
 

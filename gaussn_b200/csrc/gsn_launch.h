@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "gsn_chol_dmma.cuh"
+#include "gsn_predict.cuh"
 
 namespace gsn {
 
@@ -28,5 +29,20 @@ cudaError_t launch_logl_wide_a(int kind, const LaunchArgs* a);     // kinds 0..4
 cudaError_t launch_logl_wide_b(int kind, const LaunchArgs* a);     // kinds 5..10
 cudaError_t launch_logl_narrow_a(int kind, const LaunchArgs* a);
 cudaError_t launch_logl_narrow_b(int kind, const LaunchArgs* a);
+
+struct PredictLaunchArgs {
+  ProblemDev pd;
+  PredictDev pa;
+  const double* theta;
+  long long B, ld;
+  int* info;
+  double* workspace;
+  unsigned* counter;
+  int grid;
+  size_t smem_bytes;
+  cudaStream_t stream;
+};
+cudaError_t launch_predict_a(int kind, const PredictLaunchArgs* a);   // kinds 0..4
+cudaError_t launch_predict_b(int kind, const PredictLaunchArgs* a);   // kinds 5..10
 
 }  // namespace gsn

@@ -1,0 +1,43 @@
+// Instantiations of gsn::predict_dmma_kernel.  Compiled twice with
+//   -DGSN_SLICE_NAME=... -DGSN_SLICE_LO=.. -DGSN_SLICE_HI=..      (see gaussn_b200/build.py)
+#include "gsn_launch.h"
+#include "gsn_predict.cuh"
+
+namespace gsn {
+
+template <int KIND>
+static cudaError_t prepare_one() {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (!attr_set[dev & 63]) {
+    e = cudaFuncSetAttribute(predict_dmma_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  return cudaSuccess;
+}
+
+template <int KIND>
+static cudaError_t launch_one(const PredictLaunchArgs& a) {
+  cudaError_t e = prepare_one<KIND>();
+  if (e != cudaSuccess) return e;
+  predict_dmma_kernel<KIND><<<a.grid, CfgWide::kWarps * 32, a.smem_bytes, a.stream>>>(a.pd, a.pa, a.theta, a.B, a.ld, a.info,
+                                                                                     a.workspace, a.counter);
+  return cudaGetLastError();
+}
+
+template <int KIND>
+static cudaError_t dispatch(int kind, const PredictLaunchArgs* a) {
+  if constexpr (KIND > GSN_SLICE_HI) {
+    return cudaErrorInvalidValue;
+  } else {
+    if (kind == KIND) return a ? launch_one<KIND>(*a) : prepare_one<KIND>();
+    return dispatch<KIND + 1>(kind, a);
+  }
+}
+
+cudaError_t GSN_SLICE_NAME(int kind, const PredictLaunchArgs* a) { return dispatch<GSN_SLICE_LO>(kind, a); }
+
+}  // namespace gsn

@@ -406,24 +406,146 @@ class GP:
 
     # ------------------------------------------------------------------ prediction
     def predict(self, x_prime, x, y, yerr, band=None):
-        """Conditional mean and covariance at ``x_prime`` (gaussn/gausSN.py:362-403).
-        The three covariance blocks are evaluated by the CUDA plugin kernels and the
-        two solves run on the GPU (one Cholesky factorisation reused for both)."""
-        import torch
-        dev = torch.device("cuda", _engine.default_device() if self.device is None else self.device)
-        x_prime = np.asarray(x_prime, dtype=np.float64)
-        x = np.asarray(x, dtype=np.float64)
-        yv = torch.as_tensor(np.asarray(y, dtype=np.float64), device=dev)
-        e2 = torch.as_tensor(np.asarray(yerr, dtype=np.float64) ** 2, device=dev)
+        """Conditional mean and covariance at ``x_prime`` given observations ``(x, y, yerr)`` of a single band, for the
+        plugins' current parameters (gaussn/gausSN.py:362-403).  One launch of the prediction kernel: the
+        observations are factorised once and both moments come out of the same pass.  ``C = K + diag(yerr^2)`` must be
+        positive definite (the reference's LU solve does not check); otherwise the moments are NaN."""
+        x_prime = np.ascontiguousarray(np.asarray(x_prime, dtype=np.float64)).ravel()
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64)).ravel()
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64)).ravel()
+        yerr = np.ascontiguousarray(np.asarray(yerr, dtype=np.float64)).ravel()
         if self.kernel.kind == _engine.K_JJ:
             raise NotImplementedError("JJKernel.covariance(x, x_prime) needs equal lengths (gaussn/kernels.py:555)")
-        cov_UV = torch.as_tensor(self.kernel.covariance(x_prime, x_prime=x), device=dev)
-        cov_VV = torch.as_tensor(self.kernel.covariance(x), device=dev) + torch.diag(e2)
-        cov_UU = torch.as_tensor(self.kernel.covariance(x_prime), device=dev)
-        mu_U = torch.as_tensor(np.asarray(self.meanfunc.mean(x_prime, bands=band), dtype=np.float64), device=dev)
-        mu_V = torch.as_tensor(np.asarray(self.meanfunc.mean(x, bands=band), dtype=np.float64), device=dev)
-        rhs = torch.cat([(yv - mu_V)[:, None], cov_UV.T], dim=1)
-        sol = torch.linalg.solve(cov_VV, rhs)
-        expectation = mu_U + cov_UV @ sol[:, 0]
-        variance = cov_UU - cov_UV @ sol[:, 1:]
-        return expectation.cpu().numpy(), variance.cpu().numpy()
+        n_mean = len(self.meanfunc.params)
+        key = (x.tobytes(), y.tobytes(), yerr.tobytes(), self.kernel.kind, self.meanfunc.kind, n_mean, self.device)
+        if getattr(self, "_predict_key", None) != key:
+            if getattr(self, "_predict_problem", None) is not None:
+                self._predict_problem.close()
+            self._predict_problem = _engine.Problem(x, y, yerr, 1, 1, [0, len(x)], self.kernel.kind, self.meanfunc.kind,
+                                                    _engine.L_NONE, n_mean, self.device)
+            self._predict_key = key
+        p = self._predict_problem
+        kp = [float(v) for v in getattr(self.kernel, "params", [])][:p.n_kernel]
+        theta = np.array(kp + [float(v) for v in self.meanfunc.params], dtype=np.float64).reshape(1, -1)
+        mean_v = mean_u = None
+        if self.meanfunc.kind == _engine.M_HOST:
+            mean_v = np.asarray(self.meanfunc.mean(x, bands=band), dtype=np.float64).reshape(1, -1)
+            mean_u = np.asarray(self.meanfunc.mean(x_prime, bands=band), dtype=np.float64).reshape(1, -1)
+        e, v = _predict_chunked(p, theta, 0, len(x), x_prime, mean_v, mean_u, True)
+        return e[0], v[0]
+
+    def predict_batch(self, theta, x_prime, band=None, fix_kernel_params=False, fix_mean_params=False,
+                      fix_lensing_params=False, return_cov=True):
+        """``predict`` for every row of ``theta`` (e.g. equal-weight posterior samples) on the data set given to
+        ``optimize_parameters``, the way the reference's plotting loop uses it (gaussn/utils.py:156-209): per sample,
+        the observations of ``band`` are shifted by the sample's time delays and divided by its magnifications, and the
+        GP is conditioned on them at ``x_prime`` (epochs in the frame of the first image).  ``band`` is a band label,
+        its index in ``np.unique`` order, or ``None`` for all rows.  Returns ``expectation [B, M]`` and
+        ``variance [B, M, M]`` (``None`` with ``return_cov=False``) -- numpy for a numpy ``theta``, CUDA tensors for a
+        CUDA ``theta``.  The whole batch is one kernel launch."""
+        self._ensure_problem(self.x, self.y, self.yerr)
+        if self.lensingmodel.kind == _engine.L_NONE:
+            fix_lensing_params = True
+        ncols = self._set_map(fix_kernel_params, fix_mean_params, fix_lensing_params)
+        p = self._problem
+        if band is None:
+            row0, row1, label = 0, p.N, None
+        else:
+            labels = list(np.unique(self.bands)) if self.bands is not None else [None]
+            b = band if isinstance(band, (int, np.integer)) else labels.index(band)
+            label = labels[b]
+            row0, row1 = int(self.indices[b * self.n_images]), int(self.indices[(b + 1) * self.n_images])
+        x_prime = np.ascontiguousarray(np.asarray(x_prime, dtype=np.float64)).ravel()
+        is_dev = _is_torch_cuda(theta)
+        if is_dev:
+            import torch
+            th = theta.to(torch.float64).contiguous().reshape(-1, ncols)
+        else:
+            th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64)).reshape(-1, ncols)
+        mean_v = mean_u = None
+        if self.meanfunc.kind == _engine.M_HOST:
+            mean_v, mean_u = self._host_means_for_predict(th, row0, row1, x_prime, label)
+        e, v = _predict_chunked(p, th, row0, row1 - row0, x_prime, mean_v, mean_u, return_cov)
+        return e, v
+
+    def _host_means_for_predict(self, th, row0, row1, x_prime, label):
+        """Host mean (sncosmoMean) per theta at the shifted epochs of the band's rows and at x_prime."""
+        import torch
+        p = self._problem
+        dev = torch.device("cuda", p.device)
+        th_d = th if _is_torch_cuda(th) else torch.as_tensor(th, device=dev)
+        B = th_d.shape[0]
+        shifted = torch.empty((B, p.N), dtype=torch.float64, device=dev)
+        bvec = torch.empty((B, p.N), dtype=torch.float64, device=dev)
+        p.lens_device(th_d.data_ptr(), B, th_d.shape[1], shifted.data_ptr(), bvec.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        shifted_h, th_h = shifted.cpu().numpy()[:, row0:row1], th_d.cpu().numpy()
+        mean_cols = self._map_cols[p.n_kernel:p.n_kernel + p.n_mean]
+        bands_v = None if self.bands is None else np.asarray(self.bands)[row0:row1]
+        bands_u = None if label is None else np.repeat(label, len(x_prime))
+        mv, mu = np.empty((B, row1 - row0)), np.empty((B, len(x_prime)))
+        for i in range(B):
+            mp = None if (len(mean_cols) and mean_cols[0] < 0) else [th_h[i, c] for c in mean_cols]
+            mv[i] = self.meanfunc.mean(shifted_h[i], params=mp, bands=bands_v, zp=self.zp, zpsys=self.zpsys)
+            mu[i] = self.meanfunc.mean(x_prime, params=None, bands=bands_u, zp=self.zp, zpsys=self.zpsys)
+        return mv, mu
+
+
+def _predict_chunked(p, th, row0, n_rows, x_prime, mean_v, mean_u, want_cov):
+    """One gsn_predict_batch call when the conditioning rows and x_prime fit one factorisation (padded n_rows + M <=
+    4160); otherwise x_prime is cut into pieces and every pair of pieces is predicted jointly (the cross blocks of the
+    covariance need both)."""
+    M = len(x_prime)
+    room = _engine.MAX_ORDER - (n_rows + 31) // 32 * 32
+    if room < 2:
+        raise ValueError(f"{n_rows} conditioning epochs leave no room for prediction epochs (order limit {_engine.MAX_ORDER})")
+    if M <= room:
+        return _predict_call(p, th, row0, n_rows, x_prime, mean_v, mean_u, want_cov)
+    step = room if not want_cov else room // 2
+    cuts = list(range(0, M, step)) + [M]
+    B = th.shape[0]
+    is_dev = _is_torch_cuda(th)
+    if is_dev:
+        import torch
+        e = torch.empty((B, M), dtype=torch.float64, device=th.device)
+        v = torch.empty((B, M, M), dtype=torch.float64, device=th.device) if want_cov else None
+    else:
+        e = np.empty((B, M))
+        v = np.empty((B, M, M)) if want_cov else None
+    pieces = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
+    for a, (a0, a1) in enumerate(pieces):
+        if not want_cov:
+            e[:, a0:a1] = _predict_call(p, th, row0, n_rows, x_prime[a0:a1], mean_v, None if mean_u is None else mean_u[:, a0:a1], False)[0]
+            continue
+        for (b0, b1) in pieces[a:] if len(pieces) > 1 else [pieces[a]]:
+            same = (a0, a1) == (b0, b1)
+            sel = np.arange(a0, a1) if same else np.concatenate([np.arange(a0, a1), np.arange(b0, b1)])
+            ee, vv = _predict_call(p, th, row0, n_rows, x_prime[sel], mean_v, None if mean_u is None else mean_u[:, sel], True)
+            na = a1 - a0
+            e[:, a0:a1] = ee[:, :na]
+            v[:, a0:a1, a0:a1] = vv[:, :na, :na]
+            if not same:
+                e[:, b0:b1] = ee[:, na:]
+                v[:, b0:b1, b0:b1] = vv[:, na:, na:]
+                v[:, a0:a1, b0:b1] = vv[:, :na, na:]
+                v[:, b0:b1, a0:a1] = vv[:, na:, :na]
+    return e, v
+
+
+def _predict_call(p, th, row0, n_rows, x_prime, mean_v, mean_u, want_cov):
+    if not _is_torch_cuda(th):
+        e, v, _ = p.predict_host(th, row0, n_rows, x_prime, mean_v, mean_u, want_cov)
+        return e, v
+    import torch
+    dev = th.device
+    if dev.index != p.device:
+        raise ValueError(f"theta lives on cuda:{dev.index} but the problem is on cuda:{p.device}")
+    B, M = th.shape[0], len(x_prime)
+    xp = torch.as_tensor(np.ascontiguousarray(x_prime), device=dev)
+    mv = None if mean_v is None else torch.as_tensor(np.ascontiguousarray(mean_v), device=dev)
+    mu = None if mean_u is None else torch.as_tensor(np.ascontiguousarray(mean_u), device=dev)
+    e = torch.empty((B, M), dtype=torch.float64, device=dev)
+    v = torch.empty((B, M, M), dtype=torch.float64, device=dev) if want_cov else None
+    p.predict_device(th.data_ptr(), B, th.shape[1], row0, n_rows, xp.data_ptr(), M, e.data_ptr(), v.data_ptr() if want_cov else 0, 0,
+                     0 if mv is None else mv.data_ptr(), 0 if mu is None else mu.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.current_stream(dev).synchronize()   # xp / mv / mu are temporaries of this call
+    return e, v

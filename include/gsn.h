@@ -175,6 +175,28 @@ int gsn_logl_batch_hostmean(gsn_problem* p, const double* theta_dev, int64_t B, 
 int gsn_lens_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_t ld,
                    double* shifted_dev, double* b_dev, void* cuda_stream);
 
+/* GP.predict for a batch of theta (gaussn/gausSN.py:362-403), applied the way the reference's plotting code applies it
+ * (gaussn/utils.py:193-209): per posterior sample, to the de-lensed observations of one band.
+ *   rows [row0, row0 + n_rows) of the problem -- one band's rows, or all of them -- are the conditioning epochs: shifted
+ *     by the sample's time delays, data and errors divided by its magnifications (utils.py:202-204);
+ *   xprime_dev [M]: prediction epochs, in the frame of the reference image (delta = 0, magnification 1);
+ *   expectation_dev [B, M]  = m(x') + K(x', x~) C^-1 (y / b - m(x~)),  C = K(x~, x~) + diag((yerr / b)^2)   gausSN.py:400
+ *   variance_dev [B, M, M]  = K(x', x') - K(x', x~) C^-1 K(x~, x')     (NULL: expectation only)               gausSN.py:401
+ *   mean_v_dev [B, n_rows], mean_u_dev [B, M]: the mean function at the shifted epochs / at x', evaluated by the caller,
+ *     for GSN_M_HOST problems; NULL otherwise;
+ *   info_dev [B] or NULL: 0 ok; k > 0: C is not positive definite at pivot k (the moments are NaN; the reference's LU
+ *     solve would return numbers without meaning); -1: non-finite parameters.
+ * No band mask is applied (GP.predict has none).  n_rows rounded up to 32, plus M, must not exceed 4160.  GSN_K_JJ is not
+ * supported (the reference's K(x', x) needs len(x') == len(x), kernels.py:555).  theta follows the handle's theta map. */
+int gsn_predict_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_t ld, int64_t row0, int64_t n_rows,
+                      const double* xprime_dev, int64_t M, const double* mean_v_dev, const double* mean_u_dev,
+                      double* expectation_dev, double* variance_dev, int32_t* info_dev, void* cuda_stream);
+
+/* The same call with HOST buffers (copies inside, synchronous). */
+int gsn_predict_batch_host(gsn_problem* p, const double* theta_host, int64_t B, int64_t ld, int64_t row0, int64_t n_rows,
+                           const double* xprime_host, int64_t M, const double* mean_v_host, const double* mean_u_host,
+                           double* expectation_host, double* variance_host, int32_t* info_host);
+
 int64_t gsn_query(const gsn_problem* p, int32_t what);
 
 /* Introspection, no device needed: the order in which the work items (32x32 blocks (c, j), c >= j, of the blocked
