@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     "gsn_logl_batch_host", "gsn_logl_batch_hostmean", "gsn_lens_batch", "gsn_query", "gsn_covariance",
     "gsn_mean", "gsn_lens", "gsn_kernel_nparams", "gsn_mean_nparams", "gsn_lens_nparams",
     "gsn_abi_version", "gsn_last_error", "gsn_item_order", "gsn_logl_batch_gather",
-    "gsn_predict_batch", "gsn_predict_batch_host",
+    "gsn_predict_batch", "gsn_predict_batch_host", "gsn_predict_item_order",
 )
 MAX_ORDER = 4160   # largest padded order of a factorisation (32 * 130 block rows), also for n_rows + M of a prediction
 
@@ -94,6 +94,8 @@ def load():
         lib.gsn_lens_nparams.restype = C.c_int32
         lib.gsn_item_order.argtypes = [C.c_int64, _ip, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.c_int64]
         lib.gsn_item_order.restype = C.c_int64
+        lib.gsn_predict_item_order.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_uint32), C.c_int64]
+        lib.gsn_predict_item_order.restype = C.c_int64
         _lib = lib
         return lib
 
@@ -160,6 +162,17 @@ def item_order(N: int, band_of_row=None, n_bands: int = 1, masked: bool = False)
     out = np.empty(n, dtype=np.uint32)
     lib.gsn_item_order(N, bp, n_bands, int(masked), out.ctypes.data_as(C.POINTER(C.c_uint32)), n)
     return [(int((w >> 12) & 0xfff), int(w & 0xfff), int(w >> 24)) for w in out]
+
+
+def predict_item_order(n_rows: int, M: int, want_cov: bool = True):
+    """Work-item order of one prediction as [(c, j, is_trailing), ...] (no GPU needed)."""
+    lib = load()
+    n = lib.gsn_predict_item_order(n_rows, M, int(want_cov), None, 0)
+    if n < 0:
+        raise GsnError(lib.gsn_last_error().decode())
+    out = np.empty(n, dtype=np.uint32)
+    lib.gsn_predict_item_order(n_rows, M, int(want_cov), out.ctypes.data_as(C.POINTER(C.c_uint32)), n)
+    return [(int((w >> 12) & 0x7ff), int(w & 0xfff), bool(w & (1 << 23))) for w in out]
 
 
 # --- problem handle ---------------------------------------------------------

@@ -566,6 +566,16 @@ int64_t gsn_item_order(int64_t N, const int32_t* band_of_row, int32_t n_bands, i
   return (int64_t)items.size();
 }
 
+int64_t gsn_predict_item_order(int64_t n_rows, int64_t M, int32_t want_cov, uint32_t* out, int64_t cap) {
+  if (n_rows < 1 || M < 1) { fail(GSN_ERR_INVALID, "n_rows and M must be >= 1"); return -1; }
+  const int64_t u0 = (n_rows + 31) / 32 * 32, nblk = (u0 + M + 31) / 32;
+  if (nblk > gsn::kMaxChunks - 1) { fail(GSN_ERR_UNSUPPORTED, "order too large"); return -1; }
+  std::vector<unsigned> items((size_t)nblk * (nblk + 1) / 2);
+  const int n = gsn::make_item_order_predict((int)(u0 / 32), (int)nblk, want_cov != 0, items.data());
+  if (out) for (int64_t i = 0; i < n && i < cap; ++i) out[i] = items[i];
+  return n;
+}
+
 int64_t gsn_query(const gsn_problem* p, int32_t what) {
   if (!p) return -1;
   switch (what) {

@@ -206,6 +206,11 @@ int64_t gsn_query(const gsn_problem* p, int32_t what);
  * (lensingmodels.py:39-51) makes identically zero are not listed. */
 int64_t gsn_item_order(int64_t N, const int32_t* band_of_row, int32_t n_bands, int32_t masked, uint32_t* out, int64_t cap);
 
+/* The same for gsn_predict_batch with n_rows conditioning epochs and M prediction epochs: items of the augmented matrix
+ * (n_rows padded to 32, then the M epochs).  Bit 23 of a word marks a trailing block (both c and j among the prediction
+ * rows: accumulated and written out, neither solved nor factored); c = (word >> 12) & 0x7ff, j = word & 0xfff. */
+int64_t gsn_predict_item_order(int64_t n_rows, int64_t M, int32_t want_cov, uint32_t* out, int64_t cap);
+
 /* ---- single-call plugin evaluations (HOST pointers, synchronous) ------------ */
 
 /* kernel.covariance(x, x_prime, params): gaussn/kernels.py (each class's

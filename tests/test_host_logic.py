@@ -182,3 +182,26 @@ def test_item_order_skips_zero_blocks_of_the_band_mask(libgsn):
     # without a mask (NoLensing) the bands stay coupled: nothing is skipped
     nblk = 16
     assert len(_check_item_order(512, np.repeat([0, 1], 256), 2, False)) == nblk * (nblk + 1) // 2
+
+
+@pytest.mark.parametrize("n_rows,M,want_cov", [(1, 1, True), (48, 100, True), (64, 64, False), (70, 9, True), (512, 256, True),
+                                               (2048, 512, True), (2048, 512, False), (33, 4000, True)])
+def test_predict_item_order_is_complete_and_topological(libgsn, n_rows, M, want_cov):
+    """Prediction = partial factorisation of the augmented matrix: the conditioning block columns are factorised (all
+    rows), the trailing blocks among the prediction rows are only accumulated -- and only listed when wanted."""
+    from gaussn_b200 import _engine
+    items = _engine.predict_item_order(n_rows, M, want_cov)
+    nVb = (n_rows + 31) // 32
+    nblk = nVb + (M + 31) // 32
+    want = {(c, j, False) for c in range(nblk) for j in range(min(c, nVb - 1) + 1)}
+    want |= {(c, j, True) for c in range(nVb, nblk) for j in range(nVb, c + 1) if want_cov or c == j}
+    assert len(items) == len(set(items)) and set(items) == want
+    pos = {(c, j): i for i, (c, j, _) in enumerate(items)}
+    for (c, j, trail), i in zip(items, range(len(items))):
+        if trail:    # needs the finished rows c and j of the factorised columns
+            deps = [(c, nVb - 1), (j, nVb - 1)]
+        else:
+            deps = ([(c, j - 1), (j, j - 1)] if c != j else [(j, j - 1)]) if j > 0 else []
+            if c != j:
+                deps.append((j, j))
+        assert all(pos[d] < i for d in deps), ((c, j, trail), deps)

@@ -22,10 +22,14 @@ def main():
     from gaussn_b200 import gausSN, kernels, meanfuncs, lensingmodels
     ap = argparse.ArgumentParser()
     ap.add_argument("--samples", type=int, default=200)
+    ap.add_argument("--only", default=None, help="run one shape only (for ncu)")
+    ap.add_argument("--no-library-route", action="store_true")
     args = ap.parse_args()
     rng = np.random.default_rng(5)
     shapes = [("slsn_like", 4, 2, 194, 100), ("sweep_512", 1, 2, 512, 256), ("quasar_like", 1, 4, 2048, 512)]
     for name, n_bands, n_images, N, M in shapes:
+        if args.only and name != args.only:
+            continue
         S = n_bands * n_images
         counts = [N // S] * S
         counts[-1] += N - sum(counts)
@@ -58,6 +62,15 @@ def main():
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / reps
         n_rows = int(gp.indices[n_images] - gp.indices[0])
+        # algorithmic flops per sample and band: factorisation n^3/3, W = K_UV L^-T n^2 M, W W^T (lower half twice = full
+        # symmetric product counted once) n M^2, residual and mean 2 n^2 + 2 n M; Matern32 build 11 flop per element
+        flops = n_rows ** 3 / 3 + n_rows ** 2 * M + n_rows * M ** 2 + n_rows ** 2 + 2 * n_rows * M \
+            + 11 * ((n_rows + M) * (n_rows + M + 1) / 2)
+        tflops = flops * B * n_bands / dt / 1e12
+        if args.no_library_route:
+            print(json.dumps({"shape": name, "rows_per_band": n_rows, "M": M, "samples": B, "ms_per_figure": round(dt * 1e3, 3),
+                              "tflops": round(tflops, 2)}))
+            continue
         # the library route, per sample: three covariance blocks + LU solve (what GP.predict did before the fused kernel)
         k = min(B, 20)
         xs_d = torch.as_tensor(x[:n_rows], device="cuda")
@@ -84,6 +97,7 @@ def main():
         print(json.dumps({"shape": name, "n_bands": n_bands, "n_images": n_images, "N": N, "rows_per_band": n_rows, "M": M,
                           "samples": B, "predict_batch_ms_per_figure": round(dt * 1e3, 3),
                           "samples_x_bands_per_s": round(B * n_bands / dt, 1),
+                          "tflops_algorithmic": round(tflops, 2), "frac_of_fp64_peak_37.165": round(tflops / 37.165, 3),
                           "torch_per_sample_ms_per_figure_est": round(dt_lib * 1e3, 1), "speedup": round(dt_lib / dt, 1)}))
 
 
