@@ -308,7 +308,10 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   p->smem_wide = gsn::logl_dmma_smem_bytes<gsn::CfgWide>(pd.Npad, has_aux);
   p->smem_narrow = gsn::logl_dmma_smem_bytes<gsn::CfgNarrow>(pd.Npad, has_aux);
   if (p->smem_wide > 226 * 1024) return cleanup(fail(GSN_ERR_UNSUPPORTED, "N = %lld needs %zu bytes of shared memory", (long long)N, p->smem_wide));
-  auto ctas_per_sm = [](int cfg_ctas, size_t smem) { return std::max(1, (int)std::min<size_t>(cfg_ctas, (size_t)(227 * 1024) / (smem + 1024))); };
+  auto ctas_per_sm = [](int cfg_ctas, size_t smem) {
+    if (const char* lim = getenv("GSN_CTAS_PER_SM")) cfg_ctas = std::max(1, std::min(cfg_ctas, atoi(lim)));   // tuning hook: occupancy experiments
+    return std::max(1, (int)std::min<size_t>(cfg_ctas, (size_t)(227 * 1024) / (smem + 1024)));
+  };
   p->slot_doubles = gsn::logl_dmma_slot_doubles(pd.Npad);
   // bound the workspace to half of the free device memory for very large N
   size_t free_b = 0, total_b = 0;

@@ -103,7 +103,6 @@ predict_dmma_kernel(ProblemDev pd, PredictDev pa, const double* __restrict__ the
   const int r_in = lane >> 2, cp = (lane & 3) * 2;
 
   for (int i = tid; i < 64; i += kThreads) sh.exptab[i] = kExp2Tab[i];
-  for (int i = tid; i < kWarps * 64; i += kThreads) { (&sh.Lt[0][0])[i] = 0.0; (&sh.nWt[0][0])[i] = 0.0; }
 
   for (;;) {
     __syncthreads();
