@@ -165,7 +165,7 @@ std::vector<unsigned> build_item_list(int64_t N, const int* band_of_row, int n_b
       first_col[c] = kb;
     }
   std::vector<unsigned> items((size_t)nblk * (nblk + 1) / 2);
-  // Wide shape from N = 432: rows swept in groups of two (fewer HBM reads, clocks stay at maximum); below that
+  // Wide shape from N = 400: rows swept in groups of two (fewer HBM reads, clocks stay at maximum); below that
   // and for the narrow shape, column-major with look-ahead.  GSN_ITEM_ORDER=cols|rows and GSN_ITEM_GROUP=n are
   // tuning hooks for tools/shape_sweep.sh.  (Re-ordering the list by a simulated greedy schedule, so that no item
   // sits right behind its predecessor, was tried and lost 7 %: it breaks up the sweep that keeps HBM reads low.)

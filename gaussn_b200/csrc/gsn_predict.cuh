@@ -170,7 +170,7 @@ predict_dmma_kernel(ProblemDev pd, PredictDev pa, const double* __restrict__ the
           __syncwarp();
           if (lane == 0) st_release_shared(&sh.done[c], j + 1);
         } else {
-          DiagItem<KIND, kStages> it_;
+          DiagItem<KIND, kStages, true> it_;
           build_item<KIND, false, true>(pd, kc, sh.exptab, xs, bs, aux, c, c, lane, ring, &ag);
           it_.load_built(ring, rs, c, lane);
           if (!it_.gemm(sh, slot, nct, c, 0, c, lane, ring)) break;
@@ -194,7 +194,7 @@ predict_dmma_kernel(ProblemDev pd, PredictDev pa, const double* __restrict__ the
           }
       } else {
         // trailing diagonal block (lower triangle, mirrored) and this block's slice of the conditional mean
-        DiagItem<KIND, kStages> it_;
+        DiagItem<KIND, kStages, true> it_;
         build_item<KIND, false, true>(pd, kc, sh.exptab, xs, bs, aux, c, c, lane, ring, &ag);
         it_.load_built(ring, rs, c, lane);
         if (!it_.gemm(sh, slot, nct, c, 0, pa.nVb, lane, ring)) break;

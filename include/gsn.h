@@ -99,8 +99,8 @@ typedef enum gsn_query_what {
 } gsn_query_what;
 
 typedef enum gsn_path {
-  GSN_PATH_DMMA_BLOCKED = 1,        /* four warps per theta (N > 352, or batches below 512 thetas): blocked left-looking Cholesky, FP64 DMMA updates, L in a global workspace */
-  GSN_PATH_DMMA_BLOCKED_NARROW = 2  /* the same kernel, one warp per theta (N <= 352 and B >= 512) */
+  GSN_PATH_DMMA_BLOCKED = 1,        /* four warps per theta (N > 336, or batches below 512 thetas): blocked left-looking Cholesky, FP64 DMMA updates, L in a global workspace */
+  GSN_PATH_DMMA_BLOCKED_NARROW = 2  /* the same kernel, one warp per theta (N <= 336 and B >= 512) */
 } gsn_path;
 
 /*
