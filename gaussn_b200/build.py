@@ -20,9 +20,11 @@ HEADERS = [
     os.path.join(CSRC, "gsn_chol_dmma.cuh"),
     os.path.join(CSRC, "gsn_launch.h"),
     os.path.join(CSRC, "gsn_predict.cuh"),
+    os.path.join(CSRC, "gsn_cluster.cuh"),
     os.path.join(REPO_DIR, "include", "gsn.h"),
 ]
-SOURCES = [os.path.join(CSRC, "gsn_api.cu"), os.path.join(CSRC, "gsn_kernels.cu"), os.path.join(CSRC, "gsn_predict.cu")]
+SOURCES = [os.path.join(CSRC, "gsn_api.cu"), os.path.join(CSRC, "gsn_kernels.cu"), os.path.join(CSRC, "gsn_predict.cu"),
+           os.path.join(CSRC, "gsn_cluster.cu")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -32,14 +34,16 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-Xcompiler", "-fPIC",
 ]
-# translation units: the C ABI, four slices of likelihood-kernel instantiations ({shape} x {kinds}) and two of the
-# prediction kernel, built in parallel
+# translation units: the C ABI, four slices of likelihood-kernel instantiations ({shape} x {kinds}), two of the
+# one-theta-per-cluster kernel and two of the prediction kernel, built in parallel
 UNITS = [
     ("gsn_api", "gsn_api.cu", []),
     ("gsn_wide_a", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgWide", "-DGSN_SLICE_NAME=launch_logl_wide_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),
     ("gsn_wide_b", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgWide", "-DGSN_SLICE_NAME=launch_logl_wide_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
     ("gsn_narrow_a", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgNarrow", "-DGSN_SLICE_NAME=launch_logl_narrow_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),
     ("gsn_narrow_b", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgNarrow", "-DGSN_SLICE_NAME=launch_logl_narrow_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
+    ("gsn_cluster_a", "gsn_cluster.cu", ["-DGSN_SLICE_NAME=launch_logl_cluster_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),
+    ("gsn_cluster_b", "gsn_cluster.cu", ["-DGSN_SLICE_NAME=launch_logl_cluster_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
     ("gsn_predict_a", "gsn_predict.cu", ["-DGSN_SLICE_NAME=launch_predict_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),
     ("gsn_predict_b", "gsn_predict.cu", ["-DGSN_SLICE_NAME=launch_predict_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
 ]

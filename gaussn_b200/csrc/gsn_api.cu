@@ -16,6 +16,7 @@
 #include "gsn_device.cuh"
 #include "gsn_chol_dmma.cuh"
 #include "gsn_launch.h"
+#include "gsn_cluster.cuh"
 
 namespace {
 
@@ -65,6 +66,10 @@ struct gsn_problem {
   // chosen per call when the batch is large enough to fill the GPU with one-warp CTAs
   bool narrow_ok = false;
   int grid_wide = 0, grid_narrow = 0; size_t smem_wide = 0, smem_narrow = 0;
+  // one theta per thread-block cluster, for calls with few thetas (see gsn_cluster.cuh)
+  int cluster_max[4] = {0, 0, 0, 0};   // resident clusters of 1 << i CTAs (0: size not used for this problem)
+  size_t smem_cluster = 0;
+  unsigned* d_items_cluster = nullptr; int n_items_cluster = 0;
   int last_shape = 0;
   int n_theta_cols = 0;   // columns the caller's theta must provide
   // host staging for gsn_logl_batch_host
@@ -88,11 +93,27 @@ int dispatch_logl_out(gsn_problem* p, const double* theta, int64_t B, int64_t ld
   // One warp per theta pays off once there are enough thetas to fill the GPU with such CTAs; for small batches
   // (and single calls, which is how the reference's samplers use the likelihood) four warps per theta give the
   // lower latency (N = 141: 96 us against 161 us per call; B = 4096: 1.04 ms against 1.33 ms the other way round).
+  const int k = p->kernel_kind;
+  int cl = 0;   // log2 of the cluster size: the largest whose clusters hold all thetas of the call at once
+  for (int i = 3; i >= 1 && !cl; --i)
+    if (B <= p->cluster_max[i]) cl = i;
+  if (cl) {
+    // Few thetas: spread each over the SMs of a cluster (one theta at N = 512: 0.52 ms -> 0.22 ms per call; N = 2048:
+    // 20.8 ms -> 5.7 ms with four CTAs).
+    p->last_shape = GSN_PATH_DMMA_CLUSTER;
+    gsn::ProblemDev pd = p->pd;
+    pd.items = p->d_items_cluster; pd.n_items = p->n_items_cluster;
+    gsn::LaunchArgs a{pd, theta, B, ld, hostmean, out, info, flags, p->d_workspace, p->d_counter,
+                      (int)B << cl, p->smem_cluster, stream, 1 << cl};
+    const cudaError_t e = (k <= 4) ? gsn::launch_logl_cluster_a(k, &a, 0, 0, nullptr) : gsn::launch_logl_cluster_b(k, &a, 0, 0, nullptr);
+    if (e != cudaSuccess) return fail(GSN_ERR_CUDA, "log-likelihood cluster kernel launch failed: %s", cudaGetErrorString(e));
+    p->launches += 1;
+    return GSN_OK;
+  }
   const bool narrow = p->narrow_ok && B >= gsn::kNarrowMinBatch;
   p->last_shape = narrow ? GSN_PATH_DMMA_BLOCKED_NARROW : GSN_PATH_DMMA_BLOCKED;
   gsn::LaunchArgs a{p->pd, theta, B, ld, hostmean, out, info, flags, p->d_workspace, p->d_counter,
                     (int)std::min<int64_t>(B, narrow ? p->grid_narrow : p->grid_wide), narrow ? p->smem_narrow : p->smem_wide, stream};
-  const int k = p->kernel_kind;
   cudaError_t e;
   if (narrow) e = (k <= 4) ? gsn::launch_logl_narrow_a(k, &a) : gsn::launch_logl_narrow_b(k, &a);
   else           e = (k <= 4) ? gsn::launch_logl_wide_a(k, &a) : gsn::launch_logl_wide_b(k, &a);
@@ -324,6 +345,30 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   // load the kernel images now rather than inside the first (timed, latency-sensitive) batch call
   GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_wide_a(kernel_kind, nullptr) : gsn::launch_logl_wide_b(kernel_kind, nullptr));
   if (p->narrow_ok) GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_narrow_a(kernel_kind, nullptr) : gsn::launch_logl_narrow_b(kernel_kind, nullptr));
+  // cluster shape: cluster sizes whose warps the order can feed.  GSN_FORCE_SHAPE=cluster2|cluster4|cluster8 forces one
+  // size at any order (tests); wide / narrow switch the shape off.
+  {
+    const char* shape_env = getenv("GSN_FORCE_SHAPE");
+    p->smem_cluster = gsn::logl_cluster_smem_bytes(pd.Npad, has_aux);
+    bool any = false;
+    for (int i = 1; i <= 3 && p->smem_cluster <= 226 * 1024; ++i) {
+      bool want = N >= gsn::kClusterMinN[i];
+      if (shape_env) want = shape_env[0] == 'c' && N > 32 && atoi(shape_env + 7) == (1 << i);
+      if (!want) continue;
+      int n_cl = 0;
+      GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_cluster_a(kernel_kind, nullptr, p->smem_cluster, 1 << i, &n_cl)
+                                    : gsn::launch_logl_cluster_b(kernel_kind, nullptr, p->smem_cluster, 1 << i, &n_cl));
+      p->cluster_max[i] = std::min(n_cl, p->grid_wide);   // one workspace slot per cluster
+      any = any || n_cl > 0;
+    }
+    if (any) {
+      // column-major order with look-ahead: the widest front of independent items
+      std::vector<unsigned> citems = build_item_list(N, hband.data(), n_bands, pd.use_mask && n_bands > 1, true);
+      p->n_items_cluster = (int)citems.size();
+      GSN_CUDA_P(cudaMalloc(&p->d_items_cluster, sizeof(unsigned) * citems.size()));
+      GSN_CUDA_P(cudaMemcpy(p->d_items_cluster, citems.data(), sizeof(unsigned) * citems.size(), cudaMemcpyHostToDevice));
+    }
+  }
   GSN_CUDA_P(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
 #undef GSN_CUDA_P
   *out = p;
@@ -334,7 +379,7 @@ int gsn_problem_destroy(gsn_problem* p) {
   if (!p) return GSN_OK;
   DeviceGuard guard(p->device);
   cudaFree(p->d_x); cudaFree(p->d_y); cudaFree(p->d_yerr2); cudaFree(p->d_img); cudaFree(p->d_band);
-  cudaFree(p->d_theta_col); cudaFree(p->d_theta_fixed); cudaFree(p->d_workspace); cudaFree(p->d_counter); cudaFree(p->d_items);
+  cudaFree(p->d_theta_col); cudaFree(p->d_theta_fixed); cudaFree(p->d_workspace); cudaFree(p->d_counter); cudaFree(p->d_items); cudaFree(p->d_items_cluster);
   cudaFree(p->d_theta); cudaFree(p->d_logl); cudaFree(p->d_info);
   cudaFree(p->d_pred_ws); cudaFree(p->d_pred_items);
   if (p->h_theta) cudaFreeHost(p->h_theta);

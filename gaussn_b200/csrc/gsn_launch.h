@@ -21,6 +21,7 @@ struct LaunchArgs {
   int grid;
   size_t smem_bytes;
   cudaStream_t stream;
+  int cluster = 1;   // CTAs per theta (launch_logl_cluster_* only)
 };
 
 // Each returns cudaSuccess, a CUDA error, or cudaErrorInvalidValue if `kind` is not in its slice.
@@ -29,6 +30,11 @@ cudaError_t launch_logl_wide_a(int kind, const LaunchArgs* a);     // kinds 0..4
 cudaError_t launch_logl_wide_b(int kind, const LaunchArgs* a);     // kinds 5..10
 cudaError_t launch_logl_narrow_a(int kind, const LaunchArgs* a);
 cudaError_t launch_logl_narrow_b(int kind, const LaunchArgs* a);
+
+// One theta per thread-block cluster (gsn_cluster.cuh).  a != nullptr launches (a->grid CTAs in clusters of a->cluster);
+// a == nullptr prepares the kernel and reports how many clusters of `cluster` CTAs can be resident at once.
+cudaError_t launch_logl_cluster_a(int kind, const LaunchArgs* a, size_t smem, int cluster, int* max_clusters);   // kinds 0..4
+cudaError_t launch_logl_cluster_b(int kind, const LaunchArgs* a, size_t smem, int cluster, int* max_clusters);   // kinds 5..10
 
 struct PredictLaunchArgs {
   ProblemDev pd;

@@ -100,7 +100,8 @@ typedef enum gsn_query_what {
 
 typedef enum gsn_path {
   GSN_PATH_DMMA_BLOCKED = 1,        /* four warps per theta (N > 336, or batches below 512 thetas): blocked left-looking Cholesky, FP64 DMMA updates, L in a global workspace */
-  GSN_PATH_DMMA_BLOCKED_NARROW = 2  /* the same kernel, one warp per theta (N <= 336 and B >= 512) */
+  GSN_PATH_DMMA_BLOCKED_NARROW = 2, /* the same kernel, one warp per theta (N <= 336 and B >= 512) */
+  GSN_PATH_DMMA_CLUSTER = 3         /* latency-bound calls (N >= 256, at most as many thetas as clusters fit on the GPU): a thread-block cluster of 2, 4 or 8 four-warp CTAs, one per SM, shares one theta */
 } gsn_path;
 
 /*

@@ -450,3 +450,44 @@ def test_host_supplied_mean_with_fixed_groups(libgsn):
     # lensing fixed: theta = kernel | mean
     got = fresh().loglikelihood_batch(theta[:, :7], fix_lensing_params=True)
     assert_logl_close(got, [oracle(list(t[:2]), list(t[2:7]), l0) for t in theta], "host mean, lensing fixed")
+
+
+@pytest.mark.parametrize("kernel,n_bands,n_images,N,force", [("Matern32Kernel", 1, 2, 512, None), ("ExpSquaredKernel", 2, 2, 400, None),
+                                                             ("OUKernel", 1, 4, 1100, None), ("PeriodicKernel", 1, 2, 420, None),
+                                                             ("Matern32Kernel", 1, 2, 330, None),
+                                                             ("Matern52Kernel", 3, 2, 130, "cluster4"), ("ExpSquaredKernel", 1, 2, 70, "cluster8"),
+                                                             ("OUKernel", 2, 2, 200, "cluster2")])
+def test_cluster_shape_for_few_thetas(libgsn, monkeypatch, kernel, n_bands, n_images, N, force):
+    """Calls with a few thetas at N >= 256 spread each theta over a thread-block cluster of 2, 4 or 8 CTAs (control words
+    in the rank-0 CTA's shared memory, reached through DSMEM).  Same items, same arithmetic: bit-identical to the one-CTA
+    shape, which larger batches of the same problem use."""
+    from gaussn_b200 import _engine
+    if force:
+        monkeypatch.setenv("GSN_FORCE_SHAPE", force)
+    rng = np.random.default_rng(N * 3 + n_bands)
+    ds = _synth(rng, N, n_bands, n_images, span=4.0 * N / (n_bands * n_images))
+    theta = _theta_box(rng, 200, kernel, "UniformMean", "ConstantMagnification", n_images)
+    if kernel != "ExpSquaredKernel":
+        theta[3, 0] = -abs(theta[3, 0])          # a non-PD point among the few
+    gp = _gp_for(ds, kernel, "UniformMean", "ConstantMagnification", n_images, theta[0])
+    tail = gp.loglikelihood_batch(theta[8:24])
+    mid = gp.loglikelihood_batch(theta[1:8])
+    assert gp._problem.query(_engine.Q_PATH) == 3
+    few = np.concatenate([gp.loglikelihood_batch(theta[:1]), mid, tail])
+    assert gp._problem.query(_engine.Q_PATH) == 3
+    monkeypatch.setenv("GSN_FORCE_SHAPE", "wide")
+    gp2 = _gp_for(ds, kernel, "UniformMean", "ConstantMagnification", n_images, theta[0])
+    many = gp2.loglikelihood_batch(theta)
+    assert gp2._problem.query(_engine.Q_PATH) == 1
+    np.testing.assert_array_equal(few, many[:24])
+    if kernel != "ExpSquaredKernel":
+        assert np.isnan(few[3])
+    want = _oracle_batch(ds, theta[:12], kernel, "UniformMean", "ConstantMagnification", gp)
+    assert_logl_close(few[:12], want, f"cluster {kernel} N={N}", rtol=1e-11 if N >= 1024 else 1e-12)
+    # scalar entry point, as the reference's samplers call it
+    nk = gp_oracle.KERNEL_NPARAMS[kernel]
+    monkeypatch.delenv("GSN_FORCE_SHAPE")
+    if force:
+        monkeypatch.setenv("GSN_FORCE_SHAPE", force)
+    got = gp.jointprobability(list(theta[5]))
+    assert got == many[5] or (np.isnan(many[5]) and got == -np.inf)
