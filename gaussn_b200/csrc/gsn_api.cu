@@ -638,6 +638,9 @@ int64_t gsn_query(const gsn_problem* p, int32_t what) {
     case GSN_Q_LAUNCHES: return p->launches;
     case GSN_Q_NPAD: return p->pd.Npad;
     case GSN_Q_PATH: return p->last_shape;   // shape of the most recent launch (0 before the first)
+    case GSN_Q_CLUSTER2_MAX: return p->cluster_max[1];
+    case GSN_Q_CLUSTER4_MAX: return p->cluster_max[2];
+    case GSN_Q_CLUSTER8_MAX: return p->cluster_max[3];
   }
   return -1;
 }

@@ -95,7 +95,10 @@ typedef enum gsn_query_what {
   GSN_Q_DEVICE = 7,
   GSN_Q_LAUNCHES = 8,        /* kernels launched through this handle so far */
   GSN_Q_NPAD = 9,            /* padded matrix order used on the device */
-  GSN_Q_PATH = 10            /* launch shape of the handle's most recent batch call (gsn_path; 0 before the first) */
+  GSN_Q_PATH = 10,           /* launch shape of the handle's most recent batch call (gsn_path; 0 before the first) */
+  GSN_Q_CLUSTER2_MAX = 11,   /* largest batch that runs one theta per cluster of 2 / 4 / 8 CTAs (0: size not used at this N) */
+  GSN_Q_CLUSTER4_MAX = 12,
+  GSN_Q_CLUSTER8_MAX = 13
 } gsn_query_what;
 
 typedef enum gsn_path {

@@ -8,7 +8,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     for N in (256, 320, 384, 429, 512, 768, 1024, 2048, 4096):
         ni = 3 if N == 429 else 2
         ds = benchdata.make_dataset(N, 1, ni)
-        theta = benchdata.make_theta(64, ni)
+        theta = benchdata.make_theta(128, ni)
         gp = gausSN.GP(kernels.ExpSquaredKernel([0.3, 25.0]), meanfuncs.UniformMean([0.0]), lensingmodels.ConstantMagnification([20.0, 0.5] * (ni - 1)))
         gp.x, gp.y, gp.yerr = ds["x"], ds["y"], ds["yerr"]; gp._prepare_indices(ds["x"], ds["band"], ds["image"])
         gp.loglikelihood_batch(theta[:2])
