@@ -165,9 +165,11 @@ def item_order(N: int, band_of_row=None, n_bands: int = 1, masked: bool = False)
     return [(int((w >> 12) & 0xfff), int(w & 0xfff), int(w >> 24)) for w in out]
 
 
-def predict_item_order(n_rows: int, M: int, want_cov: bool = True):
-    """Work-item order of one prediction as [(c, j, is_trailing), ...] (no GPU needed)."""
+def predict_item_order(n_rows: int, M: int, want_cov: bool = True, cluster: bool = False):
+    """Work-item order of one prediction as [(c, j, is_trailing), ...] (no GPU needed); ``cluster`` selects the
+    column-major order used when one theta runs on a thread-block cluster."""
     lib = load()
+    want_cov = int(bool(want_cov)) | (2 if cluster else 0)
     n = lib.gsn_predict_item_order(n_rows, M, int(want_cov), None, 0)
     if n < 0:
         raise GsnError(lib.gsn_last_error().decode())

@@ -67,7 +67,8 @@ struct gsn_problem {
   bool narrow_ok = false;
   int grid_wide = 0, grid_narrow = 0; size_t smem_wide = 0, smem_narrow = 0;
   // one theta per thread-block cluster, for calls with few thetas (see gsn_cluster.cuh)
-  int cluster_max[4] = {0, 0, 0, 0};   // resident clusters of 1 << i CTAs (0: size not used for this problem)
+  int cluster_cap[4] = {0, 0, 0, 0};   // clusters of 1 << i CTAs (one CTA per SM) the device holds at once
+  int cluster_max[4] = {0, 0, 0, 0};   // largest batch evaluated one theta per cluster of 1 << i CTAs (0: size not used at this N)
   size_t smem_cluster = 0;
   unsigned* d_items_cluster = nullptr; int n_items_cluster = 0;
   int last_shape = 0;
@@ -352,12 +353,13 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
     p->smem_cluster = gsn::logl_cluster_smem_bytes(pd.Npad, has_aux);
     bool any = false;
     for (int i = 1; i <= 3 && p->smem_cluster <= 226 * 1024; ++i) {
-      bool want = N >= gsn::kClusterMinN[i];
-      if (shape_env) want = shape_env[0] == 'c' && N > 32 && atoi(shape_env + 7) == (1 << i);
-      if (!want) continue;
       int n_cl = 0;
       GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_cluster_a(kernel_kind, nullptr, p->smem_cluster, 1 << i, &n_cl)
                                     : gsn::launch_logl_cluster_b(kernel_kind, nullptr, p->smem_cluster, 1 << i, &n_cl));
+      p->cluster_cap[i] = n_cl;
+      bool want = N >= gsn::kClusterMinN[i];
+      if (shape_env) want = shape_env[0] == 'c' && N > 32 && atoi(shape_env + 7) == (1 << i);
+      if (!want) continue;
       p->cluster_max[i] = std::min(n_cl, p->grid_wide);   // one workspace slot per cluster
       any = any || n_cl > 0;
     }
@@ -539,10 +541,21 @@ int gsn_predict_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_
   pa.xprime = xprime_dev; pa.mean_v = mean_v_dev; pa.mean_u = mean_u_dev;
   pa.expectation = expectation_dev; pa.variance = variance_dev;
   // item list: cached per (padded rows, M, covariance wanted); replacing it waits for launches that may still read it
-  const long long key = ((long long)u0 << 32) | ((long long)M << 1) | (variance_dev ? 1 : 0);
+  // a call with few parameter sets (GP.predict: one) on a long light curve: one theta per thread-block cluster
+  int cl = 0;
+  {
+    const char* shape_env = getenv("GSN_FORCE_SHAPE");
+    for (int i = 3; i >= 1 && !cl; --i) {
+      bool want = pa.Npad >= gsn::kClusterMinN[i];
+      if (shape_env) want = shape_env[0] == 'c' && atoi(shape_env + 7) == (1 << i);
+      if (want && B <= p->cluster_cap[i]) cl = i;
+    }
+  }
+  const long long key = ((long long)u0 << 32) | ((long long)M << 2) | (cl ? 2 : 0) | (variance_dev ? 1 : 0);
   if (key != p->pred_key) {
     std::vector<unsigned> items((size_t)pa.nblk * (pa.nblk + 1) / 2);
-    const int n = gsn::make_item_order_predict(pa.nVb, pa.nblk, variance_dev != nullptr, items.data());
+    const int n = cl ? gsn::make_item_order_predict_cols(pa.nVb, pa.nblk, variance_dev != nullptr, items.data())
+                     : gsn::make_item_order_predict(pa.nVb, pa.nblk, variance_dev != nullptr, items.data());
     GSN_CUDA(cudaDeviceSynchronize());
     if ((size_t)n > p->pred_items_cap) {
       cudaFree(p->d_pred_items); p->d_pred_items = nullptr; p->pred_items_cap = 0;
@@ -554,11 +567,12 @@ int gsn_predict_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_
     p->pred_key = key;
   }
   pa.items = p->d_pred_items; pa.n_items = p->pred_n_items;
-  const size_t smem = gsn::predict_smem_bytes(pa.Npad);
+  size_t smem = gsn::predict_smem_bytes(pa.Npad);
   if (smem > 226 * 1024) return fail(GSN_ERR_UNSUPPORTED, "prediction of order %d needs %zu bytes of shared memory", pa.Npad, smem);
   const int ctas = std::max(1, (int)std::min<size_t>(gsn::CfgWide::kCtasPerSm, (size_t)(227 * 1024) / (smem + 1024)));
   const size_t slot_bytes = gsn::predict_slot_doubles(pa.Npad) * sizeof(double);
-  int grid = (int)std::min<int64_t>(B, (int64_t)p->sm_count * ctas);
+  int grid = (int)std::min<int64_t>(B, (int64_t)p->sm_count * ctas);   // workspace slots in use
+  if (cl) smem = gsn::predict_cluster_smem_bytes(pa.Npad);
   if ((size_t)grid * slot_bytes > p->pred_ws_bytes) {
     size_t free_b = 0, total_b = 0;
     GSN_CUDA(cudaDeviceSynchronize());
@@ -569,7 +583,8 @@ int gsn_predict_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_
     p->pred_ws_bytes = (size_t)grid * slot_bytes;
   }
   GSN_CUDA(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned), stream));
-  gsn::PredictLaunchArgs a{p->pd, pa, theta_dev, B, ld, info_dev, p->d_pred_ws, p->d_counter, grid, smem, stream};
+  gsn::PredictLaunchArgs a{p->pd, pa, theta_dev, B, ld, info_dev, p->d_pred_ws, p->d_counter, cl ? (grid << cl) : grid, smem, stream,
+                           1 << cl};
   const cudaError_t e = (k <= 4) ? gsn::launch_predict_a(k, &a) : gsn::launch_predict_b(k, &a);
   if (e != cudaSuccess) return fail(GSN_ERR_CUDA, "prediction kernel launch failed: %s", cudaGetErrorString(e));
   p->launches += 1;
@@ -619,7 +634,8 @@ int64_t gsn_predict_item_order(int64_t n_rows, int64_t M, int32_t want_cov, uint
   const int64_t u0 = (n_rows + 31) / 32 * 32, nblk = (u0 + M + 31) / 32;
   if (nblk > gsn::kMaxChunks - 1) { fail(GSN_ERR_UNSUPPORTED, "order too large"); return -1; }
   std::vector<unsigned> items((size_t)nblk * (nblk + 1) / 2);
-  const int n = gsn::make_item_order_predict((int)(u0 / 32), (int)nblk, want_cov != 0, items.data());
+  const int n = (want_cov & 2) ? gsn::make_item_order_predict_cols((int)(u0 / 32), (int)nblk, (want_cov & 1) != 0, items.data())
+                               : gsn::make_item_order_predict((int)(u0 / 32), (int)nblk, (want_cov & 1) != 0, items.data());
   if (out) for (int64_t i = 0; i < n && i < cap; ++i) out[i] = items[i];
   return n;
 }

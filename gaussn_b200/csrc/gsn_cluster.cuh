@@ -12,6 +12,7 @@
 // Per theta: cluster barrier; rank 0 finalises the previous theta, takes the next one and resets the control words;
 // cluster barrier; all CTAs pull items until the list is exhausted.
 #pragma once
+#include <algorithm>
 #include "gsn_chol_dmma.cuh"
 
 namespace gsn {

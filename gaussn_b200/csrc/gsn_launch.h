@@ -3,6 +3,7 @@
 // {launch shape} x {covariance kinds} so that the slices build in parallel).
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
 #include "gsn_chol_dmma.cuh"
 #include "gsn_predict.cuh"
 
@@ -47,6 +48,7 @@ struct PredictLaunchArgs {
   int grid;
   size_t smem_bytes;
   cudaStream_t stream;
+  int cluster = 1;   // > 1: one theta per thread-block cluster of this many CTAs (grid counts CTAs)
 };
 cudaError_t launch_predict_a(int kind, const PredictLaunchArgs* a);   // kinds 0..4
 cudaError_t launch_predict_b(int kind, const PredictLaunchArgs* a);   // kinds 5..10

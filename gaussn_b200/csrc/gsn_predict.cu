@@ -1,5 +1,6 @@
 // Instantiations of gsn::predict_dmma_kernel.  Compiled twice with
 //   -DGSN_SLICE_NAME=... -DGSN_SLICE_LO=.. -DGSN_SLICE_HI=..      (see gaussn_b200/build.py)
+#include <algorithm>
 #include "gsn_launch.h"
 #include "gsn_predict.cuh"
 
@@ -12,7 +13,9 @@ static cudaError_t prepare_one() {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (!attr_set[dev & 63]) {
-    e = cudaFuncSetAttribute(predict_dmma_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    e = cudaFuncSetAttribute(predict_dmma_kernel<KIND, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(predict_dmma_kernel<KIND, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
@@ -23,8 +26,23 @@ template <int KIND>
 static cudaError_t launch_one(const PredictLaunchArgs& a) {
   cudaError_t e = prepare_one<KIND>();
   if (e != cudaSuccess) return e;
-  predict_dmma_kernel<KIND><<<a.grid, CfgWide::kWarps * 32, a.smem_bytes, a.stream>>>(a.pd, a.pa, a.theta, a.B, a.ld, a.info,
-                                                                                     a.workspace, a.counter);
+  if (a.cluster > 1) {   // one theta per thread-block cluster of a.cluster CTAs
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr;
+    cfg.gridDim = dim3((unsigned)a.grid, 1, 1);
+    cfg.blockDim = dim3(CfgWide::kWarps * 32, 1, 1);
+    cfg.dynamicSmemBytes = a.smem_bytes;
+    cfg.stream = a.stream;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)a.cluster;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, predict_dmma_kernel<KIND, 2>, a.pd, a.pa, a.theta, a.B, a.ld, a.info, a.workspace, a.counter);
+  }
+  predict_dmma_kernel<KIND, 1><<<a.grid, CfgWide::kWarps * 32, a.smem_bytes, a.stream>>>(a.pd, a.pa, a.theta, a.B, a.ld, a.info,
+                                                                                        a.workspace, a.counter);
   return cudaGetLastError();
 }
 

@@ -21,6 +21,7 @@
 // gives NaN moments and info = index of the failing pivot, the likelihood's convention.
 #pragma once
 #include "gsn_chol_dmma.cuh"
+#include "gsn_cluster.cuh"
 
 namespace gsn {
 
@@ -68,6 +69,24 @@ inline int make_item_order_predict(int nVb, int nblk, bool want_cov, unsigned* o
   return n;
 }
 
+// Column-major variant (look-ahead on the diagonal blocks) for the cluster mode: the widest front of independent items.
+inline int make_item_order_predict_cols(int nVb, int nblk, bool want_cov, unsigned* out) {
+  int n = 0;
+  auto word = [&](int c, int j) { return ((unsigned)c << 12) | (unsigned)j; };
+  out[n++] = word(0, 0);
+  for (int j = 0; j < nVb; ++j) {
+    if (j + 1 < nblk) out[n++] = word(j + 1, j);
+    if (j + 1 < nVb) out[n++] = word(j + 1, j + 1);
+    for (int c = j + 2; c < nblk; ++c) out[n++] = word(c, j);
+  }
+  for (int c = nVb; c < nblk; ++c) {
+    if (want_cov)
+      for (int j = nVb; j < c; ++j) out[n++] = kTrailBit | word(c, j);
+    out[n++] = kTrailBit | word(c, c);
+  }
+  return n;
+}
+
 __host__ __device__ inline size_t predict_slot_doubles(int Npad) { return SlotGeom(Npad).vec_off + (size_t)5 * Npad; }
 inline size_t predict_smem_bytes(int Npad) {
   size_t b = (sizeof(CtaSharedT<CfgWide::kWarps, CfgWide::kChunks>) + 15) / 16 * 16;
@@ -76,11 +95,16 @@ inline size_t predict_smem_bytes(int Npad) {
   return b;
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(CfgWide::kWarps * 32, CfgWide::kCtasPerSm)
+inline size_t predict_cluster_smem_bytes(int Npad) { return std::max<size_t>(predict_smem_bytes(Npad), (size_t)116 * 1024); }
+
+// kCl == 1: one CTA per theta (batches of posterior samples).  kCl > 1: one theta per thread-block cluster, as in
+// gsn_cluster.cuh -- for GP.predict called with a single parameter set on a long light curve.
+template <int KIND, int kCl>
+__global__ void __launch_bounds__(CfgWide::kWarps * 32, kCl == 1 ? CfgWide::kCtasPerSm : 1)
 predict_dmma_kernel(ProblemDev pd, PredictDev pa, const double* __restrict__ theta, long long B, long long ld,
                     int* __restrict__ info, double* workspace, unsigned* counter) {
   using Cfg = CfgWide;
+  using C = Ctl<kCl>;
   constexpr int kWarps = Cfg::kWarps, kThreads = Cfg::kWarps * 32, kStages = Cfg::kStages;
   using CtaShared = CtaSharedT<Cfg::kWarps, Cfg::kChunks>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -89,7 +113,8 @@ predict_dmma_kernel(ProblemDev pd, PredictDev pa, const double* __restrict__ the
   const int Npad = pa.Npad, nblk = pa.nblk, M = pa.M;
   const SlotGeom g(Npad);
   const int nct = g.nct;
-  double* slot = workspace + (size_t)blockIdx.x * predict_slot_doubles(Npad);
+  const unsigned crank = kCl == 1 ? 0u : cluster_ctarank();
+  double* slot = workspace + (size_t)(kCl == 1 ? blockIdx.x : cluster_id_x()) * predict_slot_doubles(Npad);
   unsigned char* sp = smem_raw + (sizeof(CtaShared) + 15) / 16 * 16;
   double2* ring = reinterpret_cast<double2*>(sp) + (size_t)warp * kStages * 8 * 32 + lane;
   sp += (size_t)kWarps * kStages * 8 * 512;
@@ -104,12 +129,36 @@ predict_dmma_kernel(ProblemDev pd, PredictDev pa, const double* __restrict__ the
 
   for (int i = tid; i < 64; i += kThreads) sh.exptab[i] = kExp2Tab[i];
 
+  // a theta whose factorisation failed (C_VV not positive definite, or NaN): the moments are undefined
+  auto close_theta = [&](long long t, int failed) {
+    if (failed != 0) {
+      for (int i = tid; i < M; i += kThreads) pa.expectation[t * M + i] = nan("");
+      if (pa.variance) for (long long i = tid; i < (long long)M * M; i += kThreads) pa.variance[t * (long long)M * M + i] = nan("");
+    }
+    if (tid == 0 && info) info[t] = failed;
+  };
+
+  long long prev = -1;   // cluster mode: theta whose items have all been issued and that rank 0 still has to close
   for (;;) {
-    __syncthreads();
-    if (tid == 0) sh.next_theta = (int)atomicAdd(counter, 1u);
-    __syncthreads();
-    const long long it = sh.next_theta;
+    long long it;
+    if constexpr (kCl == 1) {
+      __syncthreads();
+      if (tid == 0) sh.next_theta = (int)atomicAdd(counter, 1u);
+      __syncthreads();
+      it = sh.next_theta;
+    } else {
+      cluster_sync_all();   // every item of the previous theta is done
+      if (crank == 0) {
+        if (prev >= 0) close_theta(prev, sh.fail);
+        __syncthreads();
+        if (tid == 0) { sh.next_theta = (int)atomicAdd(counter, 1u); sh.fail = 0; sh.next_item = 0; }
+        for (int c = tid; c <= nblk; c += kThreads) { sh.done[c] = 0; sh.rdy[c] = 0; sh.zzj[c] = 0.0; sh.ldj[c] = 0.0; }
+      }
+      cluster_sync_all();   // control words of the next theta are in place (rank 0's copy; see Ctl)
+      it = C::ld_relaxed(&sh.next_theta);
+    }
     if (it >= B) break;
+    prev = it;
     double* expct = pa.expectation + it * M;
     double* var = pa.variance ? pa.variance + it * (long long)M * M : nullptr;
 
@@ -117,8 +166,10 @@ predict_dmma_kernel(ProblemDev pd, PredictDev pa, const double* __restrict__ the
       const int col = pd.theta_col[k];
       sh.theta[k] = (col >= 0) ? theta[it * ld + col] : pd.theta_fixed[k];
     }
-    if (tid == 0) { sh.fail = 0; sh.next_item = 0; }
-    for (int c = tid; c <= nblk; c += kThreads) { sh.done[c] = 0; sh.rdy[c] = 0; sh.zzj[c] = 0.0; sh.ldj[c] = 0.0; }
+    if constexpr (kCl == 1) {
+      if (tid == 0) { sh.fail = 0; sh.next_item = 0; }
+      for (int c = tid; c <= nblk; c += kThreads) { sh.done[c] = 0; sh.rdy[c] = 0; sh.zzj[c] = 0.0; sh.ldj[c] = 0.0; }
+    }
     __syncthreads();
     const double* kp = sh.theta;
     const double* mp = sh.theta + pd.nk;
@@ -144,33 +195,32 @@ predict_dmma_kernel(ProblemDev pd, PredictDev pa, const double* __restrict__ the
       bad |= !isfinite(x_s) || !isfinite(ax);
       xs[n] = x_s; bs[n] = b; rs[n] = r; ns[n] = noise; aux[n] = ax;
     }
-    if (__syncthreads_or(bad)) {
-      for (int i = tid; i < M; i += kThreads) expct[i] = nan("");
-      if (var) for (long long i = tid; i < (long long)M * M; i += kThreads) var[i] = nan("");
-      if (tid == 0 && info) info[it] = -1;
+    if (__syncthreads_or(bad)) {   // in a cluster every CTA sees the same inputs and takes this branch together
+      if (crank == 0) close_theta(it, -1);
+      prev = -1;
       continue;
     }
 
     for (;;) {
       int idx = 0;
-      if (lane == 0) idx = atomicAdd(&sh.next_item, 1);
+      if (lane == 0) idx = C::fetch_add(&sh.next_item, 1);
       idx = __shfl_sync(0xffffffffu, idx, 0);
-      if (idx >= pa.n_items || ld_volatile_shared(&sh.fail) != 0) break;
+      if (idx >= pa.n_items || C::ld_relaxed(&sh.fail) != 0) break;
       const unsigned item = pa.items[idx];
       const bool trail = (item & kTrailBit) != 0;
       const int c = (int)((item >> 12) & 0x7ffu), j = (int)(item & 0xfffu);
       if (!trail) {
         if (c != j) {
-          OffItem<KIND, kStages> it_;
+          OffItem<KIND, kStages, kCl> it_;
           build_item<KIND, false, true>(pd, kc, sh.exptab, xs, bs, aux, c, j, lane, ring, &ag);
           it_.load_built(ring);
           if (!it_.gemm(sh, slot, nct, c, j, 0, j, lane, ring)) break;
-          if (!wait_flag(&sh.rdy[j], 0, &sh.fail)) break;
+          if (!wait_flag<kCl>(&sh.rdy[j], 0, &sh.fail)) break;
           it_.solve(slot, g, c, j, lane, ring);
           __syncwarp();
-          if (lane == 0) st_release_shared(&sh.done[c], j + 1);
+          if (lane == 0) C::st_release(&sh.done[c], j + 1);
         } else {
-          DiagItem<KIND, kStages, true> it_;
+          DiagItem<KIND, kStages, true, kCl> it_;
           build_item<KIND, false, true>(pd, kc, sh.exptab, xs, bs, aux, c, c, lane, ring, &ag);
           it_.load_built(ring, rs, c, lane);
           if (!it_.gemm(sh, slot, nct, c, 0, c, lane, ring)) break;
@@ -178,7 +228,7 @@ predict_dmma_kernel(ProblemDev pd, PredictDev pa, const double* __restrict__ the
         }
       } else if (c != j) {
         // trailing off-diagonal block: -(conditional covariance)(c, j), mirrored into (j, c)
-        OffItem<KIND, kStages> it_;
+        OffItem<KIND, kStages, kCl> it_;
         build_item<KIND, false, true>(pd, kc, sh.exptab, xs, bs, aux, c, j, lane, ring, &ag);
         it_.load_built(ring);
         if (!it_.gemm(sh, slot, nct, c, j, 0, pa.nVb, lane, ring)) break;
@@ -194,7 +244,7 @@ predict_dmma_kernel(ProblemDev pd, PredictDev pa, const double* __restrict__ the
           }
       } else {
         // trailing diagonal block (lower triangle, mirrored) and this block's slice of the conditional mean
-        DiagItem<KIND, kStages, true> it_;
+        DiagItem<KIND, kStages, true, kCl> it_;
         build_item<KIND, false, true>(pd, kc, sh.exptab, xs, bs, aux, c, c, lane, ring, &ag);
         it_.load_built(ring, rs, c, lane);
         if (!it_.gemm(sh, slot, nct, c, 0, pa.nVb, lane, ring)) break;
@@ -222,14 +272,12 @@ predict_dmma_kernel(ProblemDev pd, PredictDev pa, const double* __restrict__ the
       }
     }
 
-    __syncthreads();
-    const int failed = sh.fail;
-    if (failed != 0) {   // C_VV not positive definite (or NaN): the moments are undefined
-      for (int i = tid; i < M; i += kThreads) expct[i] = nan("");
-      if (var) for (long long i = tid; i < (long long)M * M; i += kThreads) var[i] = nan("");
+    if constexpr (kCl == 1) {
+      __syncthreads();
+      close_theta(it, sh.fail);
     }
-    if (tid == 0 && info) info[it] = failed;
   }
+  if constexpr (kCl > 1) cluster_sync_all();   // rank 0's shared memory must outlive the last remote read
 }
 
 }  // namespace gsn

@@ -214,6 +214,7 @@ int64_t gsn_item_order(int64_t N, const int32_t* band_of_row, int32_t n_bands, i
  * (n_rows padded to 32, then the M epochs).  Bit 23 of a word marks a trailing block (both c and j among the prediction
  * rows: accumulated and written out, neither solved nor factored); c = (word >> 12) & 0x7ff, j = word & 0xfff. */
 int64_t gsn_predict_item_order(int64_t n_rows, int64_t M, int32_t want_cov, uint32_t* out, int64_t cap);
+/* want_cov bit 1 (value 2 or 3) selects the column-major order used when one theta runs on a thread-block cluster. */
 
 /* ---- single-call plugin evaluations (HOST pointers, synchronous) ------------ */
 

@@ -203,3 +203,31 @@ def test_scalar_predict_matches_oracle_on_user_arrays(libgsn):
         loose = 100.0 if kname == "DotProductKernel" else 1.0
         np.testing.assert_allclose(e, e0, rtol=1e-8, atol=1e-9 * loose, err_msg=kname)
         np.testing.assert_allclose(v, v0, rtol=1e-7, atol=1e-9 * scale, err_msg=kname)
+
+
+@pytest.mark.parametrize("force", ["cluster2", "cluster4", "cluster8", None])
+def test_predict_on_a_cluster_matches_one_cta_bitwise(libgsn, monkeypatch, force):
+    """Few parameter sets on a long light curve: one theta per thread-block cluster (as the likelihood does).  Same
+    items, same arithmetic as one CTA per theta."""
+    from gaussn_b200 import gausSN, kernels, meanfuncs
+    rng = np.random.default_rng(81)
+    x = np.sort(rng.uniform(0, 900, 600))
+    y = 0.4 * np.sin(x / 40.0) + 0.03 * rng.standard_normal(600)
+    yerr = rng.uniform(0.02, 0.05, 600)
+    x_prime = np.linspace(-10, 920, 300)
+
+    def run():
+        gp = gausSN.GP(kernels.Matern32Kernel([0.3, 35.0]), meanfuncs.Sin([0.1, 0.02, 0.3]))
+        return gp.predict(x_prime, x, y, yerr)
+
+    monkeypatch.setenv("GSN_FORCE_SHAPE", "wide")
+    e1, v1 = run()
+    if force:
+        monkeypatch.setenv("GSN_FORCE_SHAPE", force)
+    else:
+        monkeypatch.delenv("GSN_FORCE_SHAPE")      # the shipped dispatch: eight CTAs for this order
+    e2, v2 = run()
+    assert np.array_equal(e1, e2) and np.array_equal(v1, v2)
+    e0, v0 = gp_oracle.predict(x_prime, x, y, yerr, "Matern32Kernel", [0.3, 35.0], "Sin", [0.1, 0.02, 0.3])
+    np.testing.assert_allclose(e2, e0, **E_TOL)
+    np.testing.assert_allclose(v2, v0, **V_TOL)

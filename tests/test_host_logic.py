@@ -186,11 +186,12 @@ def test_item_order_skips_zero_blocks_of_the_band_mask(libgsn):
 
 @pytest.mark.parametrize("n_rows,M,want_cov", [(1, 1, True), (48, 100, True), (64, 64, False), (70, 9, True), (512, 256, True),
                                                (2048, 512, True), (2048, 512, False), (33, 4000, True)])
-def test_predict_item_order_is_complete_and_topological(libgsn, n_rows, M, want_cov):
+@pytest.mark.parametrize("cluster", [False, True])
+def test_predict_item_order_is_complete_and_topological(libgsn, n_rows, M, want_cov, cluster):
     """Prediction = partial factorisation of the augmented matrix: the conditioning block columns are factorised (all
     rows), the trailing blocks among the prediction rows are only accumulated -- and only listed when wanted."""
     from gaussn_b200 import _engine
-    items = _engine.predict_item_order(n_rows, M, want_cov)
+    items = _engine.predict_item_order(n_rows, M, want_cov, cluster)
     nVb = (n_rows + 31) // 32
     nblk = nVb + (M + 31) // 32
     want = {(c, j, False) for c in range(nblk) for j in range(min(c, nVb - 1) + 1)}
