@@ -34,8 +34,6 @@ static void fill_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute& attr, int 
   cfg.numAttrs = 1;
 }
 
-
-
 template <int KIND>
 static cudaError_t launch_one(const LaunchArgs& a) {
   cudaError_t e = prepare_one<KIND>();
