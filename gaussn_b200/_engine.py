@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "gsn_logl_batch_host", "gsn_logl_batch_hostmean", "gsn_lens_batch", "gsn_query", "gsn_covariance",
     "gsn_mean", "gsn_lens", "gsn_kernel_nparams", "gsn_mean_nparams", "gsn_lens_nparams",
     "gsn_abi_version", "gsn_last_error", "gsn_item_order", "gsn_logl_batch_gather",
-    "gsn_predict_batch", "gsn_predict_batch_host", "gsn_predict_item_order",
+    "gsn_predict_batch", "gsn_predict_batch_host", "gsn_predict_item_order", "gsn_problem_set_data",
 )
 MAX_ORDER = 4160   # largest padded order of a factorisation (32 * 130 block rows), also for n_rows + M of a prediction
 
@@ -72,6 +72,7 @@ def load():
                                            _lp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         lib.gsn_problem_destroy.argtypes = [C.c_void_p]
         lib.gsn_problem_set_theta_map.argtypes = [C.c_void_p, _ip, _dp]
+        lib.gsn_problem_set_data.argtypes = [C.c_void_p, _dp, _dp, _dp]
         lib.gsn_logl_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         lib.gsn_logl_batch_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_void_p), C.c_int32, C.c_int64,
                                               C.c_void_p, C.c_uint32, C.c_void_p]
@@ -215,6 +216,13 @@ class Problem:
 
     def query(self, what: int) -> int:
         return int(self._lib.gsn_query(self._h, what))
+
+    def set_data(self, x, y, yerr):
+        """New observations of the same length and band / image structure, in place (no new handle)."""
+        x, y, yerr = _f64(x).ravel(), _f64(y).ravel(), _f64(yerr).ravel()
+        if not (len(x) == len(y) == len(yerr) == self.N):
+            raise ValueError(f"set_data needs arrays of length {self.N}")
+        _check(self._lib.gsn_problem_set_data(self._h, _ptr(x), _ptr(y), _ptr(yerr)))
 
     def set_theta_map(self, col_of_param=None, fixed_values=None):
         """``col_of_param[k]`` = column of the caller's theta feeding slot k, or -1

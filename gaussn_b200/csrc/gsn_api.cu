@@ -392,6 +392,20 @@ int gsn_problem_destroy(gsn_problem* p) {
   return GSN_OK;
 }
 
+int gsn_problem_set_data(gsn_problem* p, const double* x, const double* y, const double* yerr) {
+  if (!p) return fail(GSN_ERR_INVALID, "problem is null");
+  if (!x || !y || !yerr) return fail(GSN_ERR_INVALID, "x, y and yerr must be non-null");
+  const int N = p->pd.N, Npad = p->pd.Npad;
+  std::vector<double> hx(Npad, 0.0), hy(Npad, 0.0), he(Npad, 1.0);
+  for (int i = 0; i < N; ++i) { hx[i] = x[i]; hy[i] = y[i]; he[i] = yerr[i] * yerr[i]; }
+  DeviceGuard guard(p->device);
+  const size_t nb = sizeof(double) * Npad;
+  GSN_CUDA(cudaMemcpy(p->d_x, hx.data(), nb, cudaMemcpyHostToDevice));
+  GSN_CUDA(cudaMemcpy(p->d_y, hy.data(), nb, cudaMemcpyHostToDevice));
+  GSN_CUDA(cudaMemcpy(p->d_yerr2, he.data(), nb, cudaMemcpyHostToDevice));
+  return GSN_OK;
+}
+
 int gsn_problem_set_theta_map(gsn_problem* p, const int32_t* col_of_param, const double* fixed_values) {
   if (!p) return fail(GSN_ERR_INVALID, "problem is null");
   const int P = p->pd.P;

@@ -32,6 +32,9 @@ except ImportError:
     zeus = None
 
 
+_PREDICT_HANDLES = {}   # (N, kernel kind, mean kind, n_mean, device) -> [Problem, data key]; see GP.predict
+
+
 def _is_torch_cuda(t) -> bool:
     return type(t).__module__.startswith("torch") and getattr(t, "is_cuda", False)
 
@@ -120,6 +123,9 @@ class GP:
         n_mean = len(self.meanfunc.params)
         key = (x.tobytes(), y.tobytes(), yerr.tobytes(), self.indices.tobytes(), self.n_bands, self.n_images,
                self.kernel.kind, self.meanfunc.kind, n_mean, self.lensingmodel.kind, self.device)
+        if self._problem is not None and key != self._problem_key and key[3:] == self._problem_key[3:]:
+            self._problem.set_data(x, y, yerr)      # same structure and plugins, new observations: keep the handle
+            self._problem_key = key
         if self._problem is None or key != self._problem_key:
             if self._problem is not None:
                 self._problem.close()
@@ -416,15 +422,24 @@ class GP:
         yerr = np.ascontiguousarray(np.asarray(yerr, dtype=np.float64)).ravel()
         if self.kernel.kind == _engine.K_JJ:
             raise NotImplementedError("JJKernel.covariance(x, x_prime) needs equal lengths (gaussn/kernels.py:555)")
+        # One handle per (length, plugin kinds), kept across calls: the reference's plotting loop calls predict with
+        # fresh (shifted, de-magnified) data for every posterior sample and band (gaussn/utils.py:193-204); replacing
+        # the observations of a handle in place costs microseconds, creating one costs milliseconds.
         n_mean = len(self.meanfunc.params)
-        key = (x.tobytes(), y.tobytes(), yerr.tobytes(), self.kernel.kind, self.meanfunc.kind, n_mean, self.device)
-        if getattr(self, "_predict_key", None) != key:
-            if getattr(self, "_predict_problem", None) is not None:
-                self._predict_problem.close()
-            self._predict_problem = _engine.Problem(x, y, yerr, 1, 1, [0, len(x)], self.kernel.kind, self.meanfunc.kind,
-                                                    _engine.L_NONE, n_mean, self.device)
-            self._predict_key = key
-        p = self._predict_problem
+        key = (len(x), self.kernel.kind, self.meanfunc.kind, n_mean, self.device)
+        data_key = (x.tobytes(), y.tobytes(), yerr.tobytes())
+        cache = _PREDICT_HANDLES      # module level: that loop builds a new GP object for every sample (utils.py:193)
+        entry = cache.pop(key, None)
+        if entry is None:
+            entry = [_engine.Problem(x, y, yerr, 1, 1, [0, len(x)], self.kernel.kind, self.meanfunc.kind,
+                                     _engine.L_NONE, n_mean, self.device), data_key]
+            while len(cache) >= 8:                      # least recently used first
+                cache.pop(next(iter(cache)))[0].close()
+        elif entry[1] != data_key:
+            entry[0].set_data(x, y, yerr)
+            entry[1] = data_key
+        cache[key] = entry                               # most recently used last
+        p = entry[0]
         kp = [float(v) for v in getattr(self.kernel, "params", [])][:p.n_kernel]
         theta = np.array(kp + [float(v) for v in self.meanfunc.params], dtype=np.float64).reshape(1, -1)
         mean_v = mean_u = None

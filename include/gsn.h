@@ -130,6 +130,12 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N,
 
 int gsn_problem_destroy(gsn_problem* p);
 
+/* Replace the observations of a handle in place (same N, same band / image structure): what the reference does
+ * when its plotting loop builds a fresh GP for every posterior sample and band (gaussn/utils.py:193-204) or when
+ * optimize_parameters is called again with new data (gausSN.py:276-280) -- without paying for a new handle.
+ * No batch call on this handle may be in flight. */
+int gsn_problem_set_data(gsn_problem* p, const double* x, const double* y, const double* yerr);
+
 /*
  * fix_* handling of GP.jointprobability (gaussn/gausSN.py:173-194) without
  * host-side theta expansion.  col_of_param[k] is the column of the caller's

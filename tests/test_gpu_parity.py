@@ -491,3 +491,20 @@ def test_cluster_shape_for_few_thetas(libgsn, monkeypatch, kernel, n_bands, n_im
         monkeypatch.setenv("GSN_FORCE_SHAPE", force)
     got = gp.jointprobability(list(theta[5]))
     assert got == many[5] or (np.isnan(many[5]) and got == -np.inf)
+
+
+def test_new_observations_of_the_same_shape_reuse_the_handle(libgsn):
+    from gaussn_b200 import _engine
+    rng = np.random.default_rng(55)
+    ds = _synth(rng, 90, 2, 2)
+    theta = _theta_box(rng, 12, "Matern32Kernel", "UniformMean", "ConstantMagnification", 2)
+    gp = _gp_for(ds, "Matern32Kernel", "UniformMean", "ConstantMagnification", 2, theta[0])
+    gp.loglikelihood_batch(theta)
+    handle = gp._problem
+    y2 = ds["y"] * 1.3 + 0.05
+    e2 = ds["yerr"] * 1.3
+    got = gp.loglikelihood_batch(theta, y=y2, yerr=e2)
+    assert gp._problem is handle and handle.query(_engine.Q_LAUNCHES) == 2
+    want = gp_oracle.loglikelihood_batch(theta, ds["x"], y2, e2, "Matern32Kernel", "UniformMean", "ConstantMagnification",
+                                         gp.n_bands, gp.n_images, gp.indices)
+    assert_logl_close(got, want, "data replaced in place")

@@ -231,3 +231,26 @@ def test_predict_on_a_cluster_matches_one_cta_bitwise(libgsn, monkeypatch, force
     e0, v0 = gp_oracle.predict(x_prime, x, y, yerr, "Matern32Kernel", [0.3, 35.0], "Sin", [0.1, 0.02, 0.3])
     np.testing.assert_allclose(e2, e0, **E_TOL)
     np.testing.assert_allclose(v2, v0, **V_TOL)
+
+
+def test_scalar_predict_reuses_handles_across_gp_objects_and_data(libgsn):
+    """The reference's plotting loop builds a new GP for every posterior sample and calls predict with freshly shifted
+    data (utils.py:193-204): handles are kept per length and the observations replaced in place."""
+    from gaussn_b200 import gausSN, kernels, meanfuncs, _engine
+    rng = np.random.default_rng(91)
+    x_prime = np.linspace(0, 100, 40)
+    launches = []
+    for i in range(6):
+        N = (60, 75)[i % 2]                                  # two bands of different length, alternating
+        x = np.sort(rng.uniform(0, 100, N)) + 0.3 * i
+        y = np.sin(x / 11.0) + 0.05 * rng.standard_normal(N)
+        yerr = rng.uniform(0.03, 0.08, N)
+        kp, mp = [0.5 + 0.05 * i, 12.0 + i], [0.1 * i]
+        gp = gausSN.GP(kernels.ExpSquaredKernel(kp), meanfuncs.UniformMean(mp))
+        e, v = gp.predict(x_prime, x, y, yerr)
+        e0, v0 = gp_oracle.predict(x_prime, x, y, yerr, "ExpSquaredKernel", kp, "UniformMean", mp)
+        np.testing.assert_allclose(e, e0, **E_TOL)
+        np.testing.assert_allclose(v, v0, **V_TOL)
+        handle = gausSN._PREDICT_HANDLES[(N, _engine.K_EXPSQUARED, _engine.M_UNIFORM, 1, None)][0]
+        launches.append(handle.query(_engine.Q_LAUNCHES))
+    assert launches == [1, 1, 2, 2, 3, 3]                    # each length kept its handle
