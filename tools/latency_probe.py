@@ -1,5 +1,5 @@
 """Scalar-call and small-batch latency (the reference's samplers call the likelihood one theta at a time)."""
-import sys, os, time, json
+import sys, os, time, json, gc
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import benchdata
@@ -11,6 +11,7 @@ for N in (141, 194, 429, 512):
     gp = gausSN.GP(kernels.ExpSquaredKernel([0.3, 25.0]), meanfuncs.UniformMean([0.0]), lensingmodels.ConstantMagnification([20.0, 0.5] * (ni - 1)))
     gp.x, gp.y, gp.yerr = ds["x"], ds["y"], ds["yerr"]; gp._prepare_indices(ds["x"], ds["band"], ds["image"])
     gp.loglikelihood_batch(theta[:8])
+    gc.collect()        # the previous handle's workspace is freed now, not inside a timing loop
     row = dict(N=N, shape=os.environ.get("GSN_FORCE_SHAPE", "auto"))
     t0 = time.perf_counter(); n = 300
     for i in range(n): gp.jointprobability(list(theta[i]))
