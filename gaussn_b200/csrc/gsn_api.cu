@@ -170,9 +170,10 @@ int check_indices(const int64_t* indices, int32_t n_bands, int32_t n_images, int
   return GSN_OK;
 }
 
-// Item list of one factorisation: band structure -> first non-zero block column per chunk -> order -> list scheduling.
-// `band_of_row` has N entries (band index per row, non-decreasing) or is null (one band).
-std::vector<unsigned> build_item_list(int64_t N, const int* band_of_row, int n_bands, bool masked, bool narrow) {
+// First non-zero block column of every chunk (block row) of the factor: with a band mask (lensingmodels.py:39-51) the
+// covariance, and so its Cholesky factor, is block diagonal by band.  `band_of_row` has N entries (band index per row,
+// non-decreasing) or is null (one band).
+std::vector<int> first_block_columns(int64_t N, const int* band_of_row, int n_bands, bool masked) {
   const int nblk = (int)((N + 31) / 32);
   std::vector<int> lo(nblk), hi(nblk), first_col(nblk, 0);
   for (int c = 0; c < nblk; ++c) {
@@ -186,6 +187,22 @@ std::vector<unsigned> build_item_list(int64_t N, const int* band_of_row, int n_b
       while (kb < c && hi[kb] < lo[c]) ++kb;
       first_col[c] = kb;
     }
+  return first_col;
+}
+
+// The order that decides the launch shape: the longest block row of the factor, in rows.  One band: N.  A band mask
+// splits the factorisation into independent blocks; a theta is then as much work per item chain as its largest band.
+int64_t effective_order(int64_t N, const int* band_of_row, int n_bands, bool masked) {
+  const std::vector<int> first_col = first_block_columns(N, band_of_row, n_bands, masked);
+  int64_t span = 0;
+  for (int c = 0; c < (int)first_col.size(); ++c) span = std::max<int64_t>(span, 32 * (int64_t)(c - first_col[c] + 1));
+  return std::min(span, N);
+}
+
+// Item list of one factorisation: band structure -> first non-zero block column per chunk -> order.
+std::vector<unsigned> build_item_list(int64_t N, const int* band_of_row, int n_bands, bool masked, bool narrow) {
+  const int nblk = (int)((N + 31) / 32);
+  const std::vector<int> first_col = first_block_columns(N, band_of_row, n_bands, masked);
   std::vector<unsigned> items((size_t)nblk * (nblk + 1) / 2);
   // Wide shape from N = 400: rows swept in groups of two (fewer HBM reads, clocks stay at maximum); below that
   // and for the narrow shape, column-major with look-ahead.  GSN_ITEM_ORDER=cols|rows and GSN_ITEM_GROUP=n are
@@ -201,9 +218,11 @@ std::vector<unsigned> build_item_list(int64_t N, const int* band_of_row, int n_b
   return items;
 }
 
-bool pick_narrow(int64_t N) {
-  // one warp per theta while a theta has few work items (see CfgNarrow); GSN_FORCE_SHAPE=narrow|wide is a tuning hook
-  bool narrow = N <= gsn::kNarrowDispatchN;
+bool pick_narrow(int64_t N, int64_t n_eff) {
+  // one warp per theta while a theta has short item chains (see CfgNarrow): judged by the largest band block when a
+  // band mask splits the factorisation (4 bands x 128 rows behaves like N = 128, not 512); GSN_FORCE_SHAPE=narrow|wide
+  // is a tuning hook
+  bool narrow = n_eff <= gsn::kNarrowDispatchN && N <= gsn::kNarrowMaxN;
   if (const char* shape_env = getenv("GSN_FORCE_SHAPE")) narrow = (shape_env[0] == 'n') && N <= gsn::kNarrowMaxN;
   return narrow;
 }
@@ -279,7 +298,6 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   pd.nlog2pi = (double)N * std::log(2.0 * M_PI);
   p->n_theta_cols = pd.P;
 
-  p->narrow_ok = pick_narrow(N);
   // per-epoch tables (padded)
   std::vector<double> hx(pd.Npad, 0.0), hy(pd.Npad, 0.0), he(pd.Npad, 1.0);
   std::vector<int> himg(pd.Npad, 0), hband(pd.Npad, -1);
@@ -308,7 +326,9 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   GSN_CUDA_P(cudaMalloc(&p->d_theta_col, sizeof(int) * hcol.size()));
   GSN_CUDA_P(cudaMalloc(&p->d_theta_fixed, sizeof(double) * hfix.size()));
   GSN_CUDA_P(cudaMalloc(&p->d_counter, sizeof(unsigned)));
-  std::vector<unsigned> items = build_item_list(N, hband.data(), n_bands, pd.use_mask && n_bands > 1, p->narrow_ok);
+  const bool masked = pd.use_mask && n_bands > 1;
+  p->narrow_ok = pick_narrow(N, effective_order(N, hband.data(), n_bands, masked));
+  std::vector<unsigned> items = build_item_list(N, hband.data(), n_bands, masked, p->narrow_ok);
   pd.n_items = (int)items.size();
   {
     GSN_CUDA_P(cudaMalloc(&p->d_items, sizeof(unsigned) * items.size()));
@@ -638,7 +658,8 @@ int gsn_predict_batch_host(gsn_problem* p, const double* theta_host, int64_t B, 
 
 int64_t gsn_item_order(int64_t N, const int32_t* band_of_row, int32_t n_bands, int32_t masked, uint32_t* out, int64_t cap) {
   if (N < 1 || N > 32 * (gsn::kMaxChunks - 1) || n_bands < 1) { fail(GSN_ERR_INVALID, "bad N or n_bands"); return -1; }
-  const std::vector<unsigned> items = build_item_list(N, band_of_row, n_bands, masked != 0 && n_bands > 1, pick_narrow(N));
+  const bool m = masked != 0 && n_bands > 1;
+  const std::vector<unsigned> items = build_item_list(N, band_of_row, n_bands, m, pick_narrow(N, effective_order(N, band_of_row, n_bands, m)));
   if (out) for (int64_t i = 0; i < (int64_t)items.size() && i < cap; ++i) out[i] = items[i];
   return (int64_t)items.size();
 }
