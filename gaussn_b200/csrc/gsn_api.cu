@@ -58,7 +58,8 @@ struct gsn_problem {
   int kernel_kind = 0;
   // device buffers
   double* d_x = nullptr; double* d_y = nullptr; double* d_yerr2 = nullptr;
-  int* d_img = nullptr; int* d_band = nullptr;
+  int* d_img = nullptr; int* d_band = nullptr; int* d_rowmap = nullptr; int* d_introw = nullptr;
+  std::vector<int> h_rowmap;   // caller's row of every internal row (-1: padding); see ProblemDev
   int* d_theta_col = nullptr; double* d_theta_fixed = nullptr; unsigned* d_items = nullptr;
   double* d_workspace = nullptr; size_t slot_doubles = 0; size_t workspace_bytes = 0;
   unsigned* d_counter = nullptr;
@@ -170,16 +171,32 @@ int check_indices(const int64_t* indices, int32_t n_bands, int32_t n_images, int
   return GSN_OK;
 }
 
+// Internal row layout (see ProblemDev): rowmap[i] = caller's row of internal row i, or -1 for padding.  With a band mask
+// every band starts at a multiple of 32; without one the rows stay where they are.  The result has a multiple of 32 entries.
+// `band_of_row` has N entries (band index per row, non-decreasing) or is null (one band).
+std::vector<int> make_row_layout(int64_t N, const int* band_of_row, bool masked) {
+  std::vector<int> rowmap;
+  rowmap.reserve((size_t)N + 64);
+  for (int64_t u = 0; u < N; ++u) {
+    if (masked && band_of_row && u > 0 && band_of_row[u] != band_of_row[u - 1])
+      while (rowmap.size() % 32) rowmap.push_back(-1);
+    rowmap.push_back((int)u);
+  }
+  while (rowmap.size() % 32) rowmap.push_back(-1);
+  return rowmap;
+}
+
 // First non-zero block column of every chunk (block row) of the factor: with a band mask (lensingmodels.py:39-51) the
-// covariance, and so its Cholesky factor, is block diagonal by band.  `band_of_row` has N entries (band index per row,
-// non-decreasing) or is null (one band).
-std::vector<int> first_block_columns(int64_t N, const int* band_of_row, int n_bands, bool masked) {
-  const int nblk = (int)((N + 31) / 32);
+// covariance, and so its Cholesky factor, is block diagonal by band.  `band_int` is the band index per INTERNAL row
+// (-1 for padding rows), `n_int` rows long.
+std::vector<int> first_block_columns(const std::vector<int>& band_int, bool masked) {
+  const int nblk = (int)(band_int.size() / 32);
   std::vector<int> lo(nblk), hi(nblk), first_col(nblk, 0);
+  const int none = 1 << 30;   // a chunk of padding only counts as a band of its own
   for (int c = 0; c < nblk; ++c) {
-    const int64_t r0 = 32 * (int64_t)c, r1 = r0 + 31;
-    lo[c] = r0 < N ? (band_of_row ? band_of_row[r0] : 0) : n_bands;   // padding rows count as a band of their own
-    hi[c] = r1 < N ? (band_of_row ? band_of_row[r1] : 0) : n_bands;
+    lo[c] = none; hi[c] = none;
+    for (int r = 32 * c; r < 32 * c + 32; ++r)
+      if (band_int[r] >= 0) { if (lo[c] == none) lo[c] = band_int[r]; hi[c] = band_int[r]; }
   }
   if (masked)
     for (int c = 0; c < nblk; ++c) {
@@ -190,19 +207,26 @@ std::vector<int> first_block_columns(int64_t N, const int* band_of_row, int n_ba
   return first_col;
 }
 
+std::vector<int> internal_bands(const std::vector<int>& rowmap, const int* band_of_row) {
+  std::vector<int> b(rowmap.size(), -1);
+  for (size_t i = 0; i < rowmap.size(); ++i)
+    if (rowmap[i] >= 0) b[i] = band_of_row ? band_of_row[rowmap[i]] : 0;
+  return b;
+}
+
 // The order that decides the launch shape: the longest block row of the factor, in rows.  One band: N.  A band mask
 // splits the factorisation into independent blocks; a theta is then as much work per item chain as its largest band.
-int64_t effective_order(int64_t N, const int* band_of_row, int n_bands, bool masked) {
-  const std::vector<int> first_col = first_block_columns(N, band_of_row, n_bands, masked);
+int64_t effective_order(int64_t N, const std::vector<int>& band_int, bool masked) {
+  const std::vector<int> first_col = first_block_columns(band_int, masked);
   int64_t span = 0;
   for (int c = 0; c < (int)first_col.size(); ++c) span = std::max<int64_t>(span, 32 * (int64_t)(c - first_col[c] + 1));
   return std::min(span, N);
 }
 
 // Item list of one factorisation: band structure -> first non-zero block column per chunk -> order.
-std::vector<unsigned> build_item_list(int64_t N, const int* band_of_row, int n_bands, bool masked, bool narrow) {
-  const int nblk = (int)((N + 31) / 32);
-  const std::vector<int> first_col = first_block_columns(N, band_of_row, n_bands, masked);
+std::vector<unsigned> build_item_list(int64_t N, const std::vector<int>& band_int, bool masked, bool narrow) {
+  const int nblk = (int)(band_int.size() / 32);
+  const std::vector<int> first_col = first_block_columns(band_int, masked);
   std::vector<unsigned> items((size_t)nblk * (nblk + 1) / 2);
   // Wide shape from N = 400: rows swept in groups of two (fewer HBM reads, clocks stay at maximum); below that
   // and for the narrow shape, column-major with look-ahead.  GSN_ITEM_ORDER=cols|rows and GSN_ITEM_GROUP=n are
@@ -284,8 +308,6 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   p->kernel_kind = kernel_kind;
   gsn::ProblemDev& pd = p->pd;
   pd.N = (int)N;
-  pd.Npad = (int)((N + 31) / 32 * 32);
-  pd.nblk = pd.Npad / 32;
   pd.n_images = n_images;
   pd.n_bands = n_bands;
   pd.mean_kind = mean_kind;
@@ -298,15 +320,33 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   pd.nlog2pi = (double)N * std::log(2.0 * M_PI);
   p->n_theta_cols = pd.P;
 
-  // per-epoch tables (padded)
-  std::vector<double> hx(pd.Npad, 0.0), hy(pd.Npad, 0.0), he(pd.Npad, 1.0);
-  std::vector<int> himg(pd.Npad, 0), hband(pd.Npad, -1);
-  for (int64_t i = 0; i < N; ++i) { hx[i] = x[i]; hy[i] = y[i]; he[i] = yerr[i] * yerr[i]; }
+  // band and image of every caller's row; band-major, image-minor: gausSN.py:83-91, lensingmodels.py:94
+  std::vector<int> uimg(N, 0), uband(N, 0);
   for (int b = 0; b < n_bands; ++b)
     for (int im = 0; im < n_images; ++im) {
-      const int s = b * n_images + im;   // band-major, image-minor: gausSN.py:83-91, lensingmodels.py:94
-      for (int64_t i = indices[s]; i < indices[s + 1]; ++i) { himg[i] = im; hband[i] = b; }
+      const int s = b * n_images + im;
+      for (int64_t i = indices[s]; i < indices[s + 1]; ++i) { uimg[i] = im; uband[i] = b; }
     }
+  // internal row layout: bands aligned to 32-row chunks when the band mask applies
+  const bool masked = pd.use_mask && n_bands > 1;
+  p->h_rowmap = make_row_layout(N, uband.data(), masked);
+  const std::vector<int>& rowmap = p->h_rowmap;
+  if (rowmap.size() > (size_t)32 * (gsn::kMaxChunks - 1)) {
+    delete p;
+    return fail(GSN_ERR_UNSUPPORTED, "N = %lld in %d bands needs %zu rows once every band is aligned to 32; the limit is %d",
+                (long long)N, n_bands, rowmap.size(), 32 * (gsn::kMaxChunks - 1));
+  }
+  pd.Npad = (int)rowmap.size();
+  pd.nblk = pd.Npad / 32;
+  // per-epoch tables in the internal layout
+  std::vector<double> hx(pd.Npad, 0.0), hy(pd.Npad, 0.0), he(pd.Npad, 1.0);
+  std::vector<int> himg(pd.Npad, 0), hband(pd.Npad, -1), hintrow(N, 0);
+  for (int i = 0; i < pd.Npad; ++i) {
+    const int u = rowmap[i];
+    if (u < 0) continue;
+    hx[i] = x[u]; hy[i] = y[u]; he[i] = yerr[u] * yerr[u];
+    himg[i] = uimg[u]; hband[i] = uband[u]; hintrow[u] = i;
+  }
   std::vector<int> hcol(std::max(pd.P, 1));
   std::vector<double> hfix(std::max(pd.P, 1), 0.0);
   for (int k = 0; k < pd.P; ++k) hcol[k] = k;
@@ -323,12 +363,13 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   GSN_CUDA_P(cudaMalloc(&p->d_yerr2, nb));
   GSN_CUDA_P(cudaMalloc(&p->d_img, sizeof(int) * pd.Npad));
   GSN_CUDA_P(cudaMalloc(&p->d_band, sizeof(int) * pd.Npad));
+  GSN_CUDA_P(cudaMalloc(&p->d_rowmap, sizeof(int) * pd.Npad));
+  GSN_CUDA_P(cudaMalloc(&p->d_introw, sizeof(int) * N));
   GSN_CUDA_P(cudaMalloc(&p->d_theta_col, sizeof(int) * hcol.size()));
   GSN_CUDA_P(cudaMalloc(&p->d_theta_fixed, sizeof(double) * hfix.size()));
   GSN_CUDA_P(cudaMalloc(&p->d_counter, sizeof(unsigned)));
-  const bool masked = pd.use_mask && n_bands > 1;
-  p->narrow_ok = pick_narrow(N, effective_order(N, hband.data(), n_bands, masked));
-  std::vector<unsigned> items = build_item_list(N, hband.data(), n_bands, masked, p->narrow_ok);
+  p->narrow_ok = pick_narrow(pd.Npad, effective_order(N, hband, masked));
+  std::vector<unsigned> items = build_item_list(N, hband, masked, p->narrow_ok);
   pd.n_items = (int)items.size();
   {
     GSN_CUDA_P(cudaMalloc(&p->d_items, sizeof(unsigned) * items.size()));
@@ -340,9 +381,12 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   GSN_CUDA_P(cudaMemcpy(p->d_yerr2, he.data(), nb, cudaMemcpyHostToDevice));
   GSN_CUDA_P(cudaMemcpy(p->d_img, himg.data(), sizeof(int) * pd.Npad, cudaMemcpyHostToDevice));
   GSN_CUDA_P(cudaMemcpy(p->d_band, hband.data(), sizeof(int) * pd.Npad, cudaMemcpyHostToDevice));
+  GSN_CUDA_P(cudaMemcpy(p->d_rowmap, rowmap.data(), sizeof(int) * pd.Npad, cudaMemcpyHostToDevice));
+  GSN_CUDA_P(cudaMemcpy(p->d_introw, hintrow.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
   GSN_CUDA_P(cudaMemcpy(p->d_theta_col, hcol.data(), sizeof(int) * hcol.size(), cudaMemcpyHostToDevice));
   GSN_CUDA_P(cudaMemcpy(p->d_theta_fixed, hfix.data(), sizeof(double) * hfix.size(), cudaMemcpyHostToDevice));
   pd.x = p->d_x; pd.y = p->d_y; pd.yerr2 = p->d_yerr2; pd.img = p->d_img; pd.band = p->d_band;
+  pd.rowmap = p->d_rowmap; pd.introw = p->d_introw;
   pd.theta_col = p->d_theta_col; pd.theta_fixed = p->d_theta_fixed;
 
   // persistent grids: CTAs/SM limited by registers (launch bounds) and shared memory, for both launch shapes
@@ -385,7 +429,7 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
     }
     if (any) {
       // column-major order with look-ahead: the widest front of independent items
-      std::vector<unsigned> citems = build_item_list(N, hband.data(), n_bands, pd.use_mask && n_bands > 1, true);
+      std::vector<unsigned> citems = build_item_list(N, hband, masked, true);
       p->n_items_cluster = (int)citems.size();
       GSN_CUDA_P(cudaMalloc(&p->d_items_cluster, sizeof(unsigned) * citems.size()));
       GSN_CUDA_P(cudaMemcpy(p->d_items_cluster, citems.data(), sizeof(unsigned) * citems.size(), cudaMemcpyHostToDevice));
@@ -400,7 +444,7 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
 int gsn_problem_destroy(gsn_problem* p) {
   if (!p) return GSN_OK;
   DeviceGuard guard(p->device);
-  cudaFree(p->d_x); cudaFree(p->d_y); cudaFree(p->d_yerr2); cudaFree(p->d_img); cudaFree(p->d_band);
+  cudaFree(p->d_x); cudaFree(p->d_y); cudaFree(p->d_yerr2); cudaFree(p->d_img); cudaFree(p->d_band); cudaFree(p->d_rowmap); cudaFree(p->d_introw);
   cudaFree(p->d_theta_col); cudaFree(p->d_theta_fixed); cudaFree(p->d_workspace); cudaFree(p->d_counter); cudaFree(p->d_items); cudaFree(p->d_items_cluster);
   cudaFree(p->d_theta); cudaFree(p->d_logl); cudaFree(p->d_info);
   cudaFree(p->d_pred_ws); cudaFree(p->d_pred_items);
@@ -417,7 +461,11 @@ int gsn_problem_set_data(gsn_problem* p, const double* x, const double* y, const
   if (!x || !y || !yerr) return fail(GSN_ERR_INVALID, "x, y and yerr must be non-null");
   const int N = p->pd.N, Npad = p->pd.Npad;
   std::vector<double> hx(Npad, 0.0), hy(Npad, 0.0), he(Npad, 1.0);
-  for (int i = 0; i < N; ++i) { hx[i] = x[i]; hy[i] = y[i]; he[i] = yerr[i] * yerr[i]; }
+  for (int i = 0; i < Npad; ++i) {
+    const int u = p->h_rowmap[i];
+    if (u >= 0) { hx[i] = x[u]; hy[i] = y[u]; he[i] = yerr[u] * yerr[u]; }
+  }
+  (void)N;
   DeviceGuard guard(p->device);
   const size_t nb = sizeof(double) * Npad;
   GSN_CUDA(cudaMemcpy(p->d_x, hx.data(), nb, cudaMemcpyHostToDevice));
@@ -659,7 +707,10 @@ int gsn_predict_batch_host(gsn_problem* p, const double* theta_host, int64_t B, 
 int64_t gsn_item_order(int64_t N, const int32_t* band_of_row, int32_t n_bands, int32_t masked, uint32_t* out, int64_t cap) {
   if (N < 1 || N > 32 * (gsn::kMaxChunks - 1) || n_bands < 1) { fail(GSN_ERR_INVALID, "bad N or n_bands"); return -1; }
   const bool m = masked != 0 && n_bands > 1;
-  const std::vector<unsigned> items = build_item_list(N, band_of_row, n_bands, m, pick_narrow(N, effective_order(N, band_of_row, n_bands, m)));
+  const std::vector<int> rowmap = make_row_layout(N, band_of_row, m);
+  if (rowmap.size() > (size_t)32 * (gsn::kMaxChunks - 1)) { fail(GSN_ERR_UNSUPPORTED, "too many rows once the bands are aligned"); return -1; }
+  const std::vector<int> band_int = internal_bands(rowmap, band_of_row);
+  const std::vector<unsigned> items = build_item_list(N, band_int, m, pick_narrow((int64_t)rowmap.size(), effective_order(N, band_int, m)));
   if (out) for (int64_t i = 0; i < (int64_t)items.size() && i < cap; ++i) out[i] = items[i];
   return (int64_t)items.size();
 }

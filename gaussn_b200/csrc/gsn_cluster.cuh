@@ -105,9 +105,10 @@ logl_cluster_kernel(ProblemDev pd, const double* __restrict__ theta, long long B
     int bad = (tid == 0) && !(isfinite(kc.amp) && isfinite(kc.c1) && isfinite(kc.c2) && isfinite(kc.c3) && isfinite(kc.c4));
     for (int n = tid; n < Npad; n += kThreads) {
       double x_s = 0.0, b = 0.0, r = 0.0, ax = 0.0;
-      if (n < pd.N) {
+      const int u = pd.rowmap[n];
+      if (u >= 0) {
         lens_eval(pd.lens_kind, lp, pd.img[n], pd.x[n], x_s, b);
-        const double m = hostmean ? hostmean[it * pd.N + n] : mean_eval(pd.mean_kind, mp, x_s);
+        const double m = hostmean ? hostmean[it * pd.N + u] : mean_eval(pd.mean_kind, mp, x_s);
         r = b * m - pd.y[n];
         if (kernel_has_aux<KIND>()) ax = kernel_aux<KIND>(kc, x_s);
         bad |= !isfinite(x_s) || !isfinite(ax);

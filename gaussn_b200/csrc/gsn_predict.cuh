@@ -181,7 +181,7 @@ predict_dmma_kernel(ProblemDev pd, PredictDev pa, const double* __restrict__ the
     for (int n = tid; n < Npad; n += kThreads) {
       double x_s = 0.0, b = 0.0, r = 0.0, noise = 0.0, ax = 0.0;
       if (n < pa.nV) {            // observed epoch: shifted, magnified (gausSN.py:139-142; utils.py:202-204)
-        const int row = pa.row0 + n;
+        const int row = pd.introw[pa.row0 + n];
         lens_eval(pd.lens_kind, lp, pd.img[row], pd.x[row], x_s, b);
         const double m = pa.mean_v ? pa.mean_v[it * pa.nV + n] : mean_eval(pd.mean_kind, mp, x_s);
         r = b * m - pd.y[row];

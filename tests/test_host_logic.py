@@ -139,20 +139,21 @@ def test_bench_flop_model():
 
 def _check_item_order(N, band_of_row, n_bands, masked):
     """Every non-zero block exactly once, and every item after everything it waits for (the kernel's
-    warps pull items in this order and spin on unfinished predecessors: a non-topological list could deadlock)."""
+    warps pull items in this order and spin on unfinished predecessors: a non-topological list could deadlock).
+    With a band mask the rows are laid out with every band starting at a multiple of 32, so that no chunk couples
+    two bands: the factor is then exactly block diagonal at chunk granularity."""
     from gaussn_b200 import _engine
     items = _engine.item_order(N, band_of_row, n_bands, masked)
-    nblk = (N + 31) // 32
     band = np.zeros(N, dtype=int) if band_of_row is None else np.asarray(band_of_row)
-    lo = [band[32 * c] if 32 * c < N else n_bands for c in range(nblk)]
-    hi = [band[32 * c + 31] if 32 * c + 31 < N else n_bands for c in range(nblk)]
-    first = [0] * nblk
-    if masked and n_bands > 1:
-        for c in range(nblk):
-            kb = 0
-            while kb < c and hi[kb] < lo[c]:
-                kb += 1
-            first[c] = kb
+    use_mask = masked and n_bands > 1
+    if use_mask:
+        chunk_band = []
+        for b in range(n_bands):
+            chunk_band += [b] * ((int(np.sum(band == b)) + 31) // 32)
+    else:
+        chunk_band = [0] * ((N + 31) // 32)
+    nblk = len(chunk_band)
+    first = [chunk_band.index(chunk_band[c]) if use_mask else 0 for c in range(nblk)]
     want = {(c, j) for c in range(nblk) for j in range(first[c], c + 1)}
     got = [(c, j) for c, j, _ in items]
     assert len(got) == len(set(got)) and set(got) == want
