@@ -42,6 +42,8 @@ UNITS = [
     ("gsn_wide_b", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgWide", "-DGSN_SLICE_NAME=launch_logl_wide_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
     ("gsn_narrow_a", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgNarrow", "-DGSN_SLICE_NAME=launch_logl_narrow_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),
     ("gsn_narrow_b", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgNarrow", "-DGSN_SLICE_NAME=launch_logl_narrow_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
+    ("gsn_tiny_a", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgTiny", "-DGSN_SLICE_NAME=launch_logl_tiny_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),
+    ("gsn_tiny_b", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgTiny", "-DGSN_SLICE_NAME=launch_logl_tiny_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
     ("gsn_cluster_a", "gsn_cluster.cu", ["-DGSN_SLICE_NAME=launch_logl_cluster_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),
     ("gsn_cluster_b", "gsn_cluster.cu", ["-DGSN_SLICE_NAME=launch_logl_cluster_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
     ("gsn_predict_a", "gsn_predict.cu", ["-DGSN_SLICE_NAME=launch_predict_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),

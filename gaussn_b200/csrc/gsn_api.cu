@@ -66,6 +66,7 @@ struct gsn_problem {
   // two launch shapes (see CfgWide / CfgNarrow): the narrow one is available for N <= kNarrowDispatchN and is
   // chosen per call when the batch is large enough to fill the GPU with one-warp CTAs
   bool narrow_ok = false;
+  bool tiny_ok = false; int grid_tiny = 0; size_t smem_tiny = 0;   // the one-warp shape at 12 CTAs per SM, N <= 96
   int grid_wide = 0, grid_narrow = 0; size_t smem_wide = 0, smem_narrow = 0;
   // one theta per thread-block cluster, for calls with few thetas (see gsn_cluster.cuh)
   int cluster_cap[4] = {0, 0, 0, 0};   // clusters of 1 << i CTAs (one CTA per SM) the device holds at once
@@ -114,10 +115,13 @@ int dispatch_logl_out(gsn_problem* p, const double* theta, int64_t B, int64_t ld
   }
   const bool narrow = p->narrow_ok && B >= gsn::kNarrowMinBatch;
   p->last_shape = narrow ? GSN_PATH_DMMA_BLOCKED_NARROW : GSN_PATH_DMMA_BLOCKED;
+  const bool tiny = narrow && p->tiny_ok;
   gsn::LaunchArgs a{p->pd, theta, B, ld, hostmean, out, info, flags, p->d_workspace, p->d_counter,
-                    (int)std::min<int64_t>(B, narrow ? p->grid_narrow : p->grid_wide), narrow ? p->smem_narrow : p->smem_wide, stream};
+                    (int)std::min<int64_t>(B, tiny ? p->grid_tiny : narrow ? p->grid_narrow : p->grid_wide),
+                    tiny ? p->smem_tiny : narrow ? p->smem_narrow : p->smem_wide, stream};
   cudaError_t e;
-  if (narrow) e = (k <= 4) ? gsn::launch_logl_narrow_a(k, &a) : gsn::launch_logl_narrow_b(k, &a);
+  if (tiny) e = (k <= 4) ? gsn::launch_logl_tiny_a(k, &a) : gsn::launch_logl_tiny_b(k, &a);
+  else if (narrow) e = (k <= 4) ? gsn::launch_logl_narrow_a(k, &a) : gsn::launch_logl_narrow_b(k, &a);
   else           e = (k <= 4) ? gsn::launch_logl_wide_a(k, &a) : gsn::launch_logl_wide_b(k, &a);
   if (e != cudaSuccess) return fail(GSN_ERR_CUDA, "log-likelihood kernel launch failed: %s", cudaGetErrorString(e));
   p->launches += 1;
@@ -405,11 +409,15 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   const size_t max_slots = std::max<size_t>(1, (free_b / 2) / (p->slot_doubles * sizeof(double)));
   p->grid_wide = (int)std::min<size_t>((size_t)p->sm_count * ctas_per_sm(gsn::CfgWide::kCtasPerSm, p->smem_wide), max_slots);
   p->grid_narrow = p->narrow_ok ? (int)std::min<size_t>((size_t)p->sm_count * ctas_per_sm(gsn::CfgNarrow::kCtasPerSm, p->smem_narrow), max_slots) : 0;
-  p->workspace_bytes = (size_t)std::max(p->grid_wide, p->grid_narrow) * p->slot_doubles * sizeof(double);
+  p->tiny_ok = p->narrow_ok && pd.Npad <= gsn::kTinyMaxN;
+  p->smem_tiny = gsn::logl_dmma_smem_bytes<gsn::CfgTiny>(pd.Npad, has_aux);
+  p->grid_tiny = p->tiny_ok ? (int)std::min<size_t>((size_t)p->sm_count * ctas_per_sm(gsn::CfgTiny::kCtasPerSm, p->smem_tiny), max_slots) : 0;
+  p->workspace_bytes = (size_t)std::max(std::max(p->grid_wide, p->grid_narrow), p->grid_tiny) * p->slot_doubles * sizeof(double);
   GSN_CUDA_P(cudaMalloc(&p->d_workspace, p->workspace_bytes));
   // load the kernel images now rather than inside the first (timed, latency-sensitive) batch call
   GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_wide_a(kernel_kind, nullptr) : gsn::launch_logl_wide_b(kernel_kind, nullptr));
-  if (p->narrow_ok) GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_narrow_a(kernel_kind, nullptr) : gsn::launch_logl_narrow_b(kernel_kind, nullptr));
+  if (p->narrow_ok && !p->tiny_ok) GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_narrow_a(kernel_kind, nullptr) : gsn::launch_logl_narrow_b(kernel_kind, nullptr));
+  if (p->tiny_ok) GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_tiny_a(kernel_kind, nullptr) : gsn::launch_logl_tiny_b(kernel_kind, nullptr));
   // cluster shape: cluster sizes whose warps the order can feed.  GSN_FORCE_SHAPE=cluster2|cluster4|cluster8 forces one
   // size at any order (tests); wide / narrow switch the shape off.
   {
@@ -735,7 +743,7 @@ int64_t gsn_query(const gsn_problem* p, int32_t what) {
     case GSN_Q_NPARAMS_MEAN: return p->pd.nm;
     case GSN_Q_NPARAMS_LENS: return p->pd.nl;
     case GSN_Q_WORKSPACE_BYTES: return (int64_t)p->workspace_bytes;
-    case GSN_Q_GRID: return std::max(p->grid_wide, p->grid_narrow);
+    case GSN_Q_GRID: return std::max(std::max(p->grid_wide, p->grid_narrow), p->grid_tiny);
     case GSN_Q_DEVICE: return p->device;
     case GSN_Q_LAUNCHES: return p->launches;
     case GSN_Q_NPAD: return p->pd.Npad;

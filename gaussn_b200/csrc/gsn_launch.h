@@ -31,6 +31,8 @@ cudaError_t launch_logl_wide_a(int kind, const LaunchArgs* a);     // kinds 0..4
 cudaError_t launch_logl_wide_b(int kind, const LaunchArgs* a);     // kinds 5..10
 cudaError_t launch_logl_narrow_a(int kind, const LaunchArgs* a);
 cudaError_t launch_logl_narrow_b(int kind, const LaunchArgs* a);
+cudaError_t launch_logl_tiny_a(int kind, const LaunchArgs* a);
+cudaError_t launch_logl_tiny_b(int kind, const LaunchArgs* a);
 
 // One theta per thread-block cluster (gsn_cluster.cuh).  a != nullptr launches (a->grid CTAs in clusters of a->cluster);
 // a == nullptr prepares the kernel and reports how many clusters of `cluster` CTAs can be resident at once.

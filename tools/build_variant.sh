@@ -12,6 +12,8 @@ nvcc $F -DGSN_SLICE_CFG=CfgWide -DGSN_SLICE_NAME=launch_logl_wide_a -DGSN_SLICE_
 nvcc $F -DGSN_SLICE_CFG=CfgWide -DGSN_SLICE_NAME=launch_logl_wide_b -DGSN_SLICE_LO=5 -DGSN_SLICE_HI=10 -c -o $T/wb.o gsn_kernels.cu &
 nvcc $F -DGSN_SLICE_CFG=CfgNarrow -DGSN_SLICE_NAME=launch_logl_narrow_a -DGSN_SLICE_LO=0 -DGSN_SLICE_HI=4 -c -o $T/na.o gsn_kernels.cu &
 nvcc $F -DGSN_SLICE_CFG=CfgNarrow -DGSN_SLICE_NAME=launch_logl_narrow_b -DGSN_SLICE_LO=5 -DGSN_SLICE_HI=10 -c -o $T/nb.o gsn_kernels.cu &
+nvcc $F -DGSN_SLICE_CFG=CfgTiny -DGSN_SLICE_NAME=launch_logl_tiny_a -DGSN_SLICE_LO=0 -DGSN_SLICE_HI=4 -c -o $T/ta.o gsn_kernels.cu &
+nvcc $F -DGSN_SLICE_CFG=CfgTiny -DGSN_SLICE_NAME=launch_logl_tiny_b -DGSN_SLICE_LO=5 -DGSN_SLICE_HI=10 -c -o $T/tb.o gsn_kernels.cu &
 nvcc $F -DGSN_SLICE_NAME=launch_logl_cluster_a -DGSN_SLICE_LO=0 -DGSN_SLICE_HI=4 -c -o $T/ca.o gsn_cluster.cu &
 nvcc $F -DGSN_SLICE_NAME=launch_logl_cluster_b -DGSN_SLICE_LO=5 -DGSN_SLICE_HI=10 -c -o $T/cb.o gsn_cluster.cu &
 nvcc $F -DGSN_SLICE_NAME=launch_predict_a -DGSN_SLICE_LO=0 -DGSN_SLICE_HI=4 -c -o $T/pa.o gsn_predict.cu &
