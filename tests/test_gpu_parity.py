@@ -509,3 +509,35 @@ def test_new_observations_of_the_same_shape_reuse_the_handle(libgsn):
     want = gp_oracle.loglikelihood_batch(theta, ds["x"], y2, e2, "Matern32Kernel", "UniformMean", "ConstantMagnification",
                                          gp.n_bands, gp.n_images, gp.indices)
     assert_logl_close(got, want, "data replaced in place")
+
+
+def test_handles_on_different_threads_run_concurrently(libgsn):
+    """include/gsn.h: a handle is not thread-safe, but different handles may be driven from different threads at the
+    same time (each host-buffer call runs on its handle's own stream).  Results must not depend on what else runs."""
+    import threading
+    rng = np.random.default_rng(66)
+    jobs = []
+    for kernel, n_bands, n_images, N, B in (("ExpSquaredKernel", 1, 2, 141, 700), ("Matern32Kernel", 4, 2, 194, 64),
+                                            ("OUKernel", 1, 3, 429, 5), ("Matern52Kernel", 2, 2, 520, 150)):
+        ds = _synth(rng, N, n_bands, n_images, span=4.0 * N / (n_bands * n_images))
+        theta = _theta_box(rng, B, kernel, "UniformMean", "ConstantMagnification", n_images)
+        gp = _gp_for(ds, kernel, "UniformMean", "ConstantMagnification", n_images, theta[0])
+        jobs.append((gp, theta, gp.loglikelihood_batch(theta)))      # serial reference (also creates the handle)
+    errors = []
+
+    def worker(gp, theta, want):
+        try:
+            for _ in range(25):
+                got = gp.loglikelihood_batch(theta)
+                if not np.array_equal(got, want):
+                    errors.append("mismatch")
+                    return
+        except Exception as e:   # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=job) for job in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
