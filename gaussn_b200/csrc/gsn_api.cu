@@ -90,6 +90,20 @@ struct gsn_problem {
 
 namespace {
 
+// The factor workspace grows on demand: one slot per CTA (or cluster) a call actually launches, so that a handle used one
+// theta at a time -- or only for prediction -- never pays for the 444 slots of a full batch (59 GB at N = 4096).  Growing
+// waits for whatever still uses the old allocation.
+int ensure_workspace(gsn_problem* p, int64_t slots) {
+  const size_t need = (size_t)slots * p->slot_doubles * sizeof(double);
+  if (need <= p->workspace_bytes) return GSN_OK;
+  GSN_CUDA(cudaDeviceSynchronize());
+  cudaFree(p->d_workspace);
+  p->d_workspace = nullptr; p->workspace_bytes = 0;
+  GSN_CUDA(cudaMalloc(&p->d_workspace, need));
+  p->workspace_bytes = need;
+  return GSN_OK;
+}
+
 int dispatch_logl_out(gsn_problem* p, const double* theta, int64_t B, int64_t ld, const double* hostmean,
                       const gsn::GatherOut& out, int* info, unsigned flags, cudaStream_t stream) {
   GSN_CUDA(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned), stream));
@@ -104,6 +118,7 @@ int dispatch_logl_out(gsn_problem* p, const double* theta, int64_t B, int64_t ld
     // Few thetas: spread each over the SMs of a cluster (one theta at N = 512: 0.52 ms -> 0.22 ms per call; N = 2048:
     // 20.8 ms -> 5.7 ms with four CTAs).
     p->last_shape = GSN_PATH_DMMA_CLUSTER;
+    if (int rc = ensure_workspace(p, B)) return rc;
     gsn::ProblemDev pd = p->pd;
     pd.items = p->d_items_cluster; pd.n_items = p->n_items_cluster;
     gsn::LaunchArgs a{pd, theta, B, ld, hostmean, out, info, flags, p->d_workspace, p->d_counter,
@@ -116,8 +131,9 @@ int dispatch_logl_out(gsn_problem* p, const double* theta, int64_t B, int64_t ld
   const bool narrow = p->narrow_ok && B >= gsn::kNarrowMinBatch;
   p->last_shape = narrow ? GSN_PATH_DMMA_BLOCKED_NARROW : GSN_PATH_DMMA_BLOCKED;
   const bool tiny = narrow && p->tiny_ok;
-  gsn::LaunchArgs a{p->pd, theta, B, ld, hostmean, out, info, flags, p->d_workspace, p->d_counter,
-                    (int)std::min<int64_t>(B, tiny ? p->grid_tiny : narrow ? p->grid_narrow : p->grid_wide),
+  const int grid = (int)std::min<int64_t>(B, tiny ? p->grid_tiny : narrow ? p->grid_narrow : p->grid_wide);
+  if (int rc = ensure_workspace(p, grid)) return rc;
+  gsn::LaunchArgs a{p->pd, theta, B, ld, hostmean, out, info, flags, p->d_workspace, p->d_counter, grid,
                     tiny ? p->smem_tiny : narrow ? p->smem_narrow : p->smem_wide, stream};
   cudaError_t e;
   if (tiny) e = (k <= 4) ? gsn::launch_logl_tiny_a(k, &a) : gsn::launch_logl_tiny_b(k, &a);
@@ -412,8 +428,7 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   p->tiny_ok = p->narrow_ok && pd.Npad <= gsn::kTinyMaxN;
   p->smem_tiny = gsn::logl_dmma_smem_bytes<gsn::CfgTiny>(pd.Npad, has_aux);
   p->grid_tiny = p->tiny_ok ? (int)std::min<size_t>((size_t)p->sm_count * ctas_per_sm(gsn::CfgTiny::kCtasPerSm, p->smem_tiny), max_slots) : 0;
-  p->workspace_bytes = (size_t)std::max(std::max(p->grid_wide, p->grid_narrow), p->grid_tiny) * p->slot_doubles * sizeof(double);
-  GSN_CUDA_P(cudaMalloc(&p->d_workspace, p->workspace_bytes));
+  // the workspace itself is allocated by the first batch call (ensure_workspace)
   // load the kernel images now rather than inside the first (timed, latency-sensitive) batch call
   GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_wide_a(kernel_kind, nullptr) : gsn::launch_logl_wide_b(kernel_kind, nullptr));
   if (p->narrow_ok && !p->tiny_ok) GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_narrow_a(kernel_kind, nullptr) : gsn::launch_logl_narrow_b(kernel_kind, nullptr));

@@ -90,7 +90,7 @@ typedef enum gsn_query_what {
   GSN_Q_NPARAMS_KERNEL = 2,
   GSN_Q_NPARAMS_MEAN = 3,
   GSN_Q_NPARAMS_LENS = 4,
-  GSN_Q_WORKSPACE_BYTES = 5, /* device workspace owned by the handle */
+  GSN_Q_WORKSPACE_BYTES = 5, /* device workspace owned by the handle so far (it grows with the largest batch evaluated) */
   GSN_Q_GRID = 6,            /* persistent CTAs launched per batch call */
   GSN_Q_DEVICE = 7,
   GSN_Q_LAUNCHES = 8,        /* kernels launched through this handle so far */

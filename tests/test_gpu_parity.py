@@ -541,3 +541,23 @@ def test_handles_on_different_threads_run_concurrently(libgsn):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_workspace_grows_with_the_largest_batch(libgsn):
+    """A handle used one theta at a time (or only for prediction) holds a workspace for the CTAs it launched, not for a
+    full batch; a larger batch grows it, results are unaffected."""
+    from gaussn_b200 import _engine
+    rng = np.random.default_rng(77)
+    ds = _synth(rng, 300, 1, 2)
+    theta = _theta_box(rng, 900, "Matern32Kernel", "UniformMean", "ConstantMagnification", 2)
+    gp = _gp_for(ds, "Matern32Kernel", "UniformMean", "ConstantMagnification", 2, theta[0])
+    one = gp.loglikelihood_batch(theta[:1])
+    w1 = gp._problem.query(_engine.Q_WORKSPACE_BYTES)
+    mid = gp.loglikelihood_batch(theta[:200])
+    w2 = gp._problem.query(_engine.Q_WORKSPACE_BYTES)
+    big = gp.loglikelihood_batch(theta)
+    w3 = gp._problem.query(_engine.Q_WORKSPACE_BYTES)
+    assert 0 < w1 < w2 < w3
+    again = gp.loglikelihood_batch(theta[:1])
+    assert gp._problem.query(_engine.Q_WORKSPACE_BYTES) == w3
+    assert one[0] == big[0] == again[0] and np.array_equal(mid, big[:200])
