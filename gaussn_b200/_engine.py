@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = (
     "gsn_abi_version", "gsn_last_error", "gsn_item_order", "gsn_logl_batch_gather",
     "gsn_predict_batch", "gsn_predict_batch_host", "gsn_predict_item_order", "gsn_problem_set_data",
 )
-MAX_ORDER = 4160   # largest padded order of a factorisation (32 * 130 block rows), also for n_rows + M of a prediction
+MAX_ORDER = 8128   # largest padded order of a factorisation (32 * 254 block rows), also for n_rows + M of a prediction
 
 
 class GsnError(RuntimeError):

@@ -507,7 +507,7 @@ class GP:
 
 def _predict_chunked(p, th, row0, n_rows, x_prime, mean_v, mean_u, want_cov):
     """One gsn_predict_batch call when the conditioning rows and x_prime fit one factorisation (padded n_rows + M <=
-    4160); otherwise x_prime is cut into pieces and every pair of pieces is predicted jointly (the cross blocks of the
+    8128); otherwise x_prime is cut into pieces and every pair of pieces is predicted jointly (the cross blocks of the
     covariance need both)."""
     M = len(x_prime)
     room = _engine.MAX_ORDER - (n_rows + 31) // 32 * 32

@@ -196,7 +196,7 @@ int gsn_lens_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_t l
  *     for GSN_M_HOST problems; NULL otherwise;
  *   info_dev [B] or NULL: 0 ok; k > 0: C is not positive definite at pivot k (the moments are NaN; the reference's LU
  *     solve would return numbers without meaning); -1: non-finite parameters.
- * No band mask is applied (GP.predict has none).  n_rows rounded up to 32, plus M, must not exceed 4160.  GSN_K_JJ is not
+ * No band mask is applied (GP.predict has none).  n_rows rounded up to 32, plus M, must not exceed 8192.  GSN_K_JJ is not
  * supported (the reference's K(x', x) needs len(x') == len(x), kernels.py:555).  theta follows the handle's theta map. */
 int gsn_predict_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_t ld, int64_t row0, int64_t n_rows,
                       const double* xprime_dev, int64_t M, const double* mean_v_dev, const double* mean_u_dev,

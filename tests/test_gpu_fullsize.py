@@ -85,13 +85,13 @@ def test_headline_shape_at_the_shipped_cadence(libgsn):
     assert np.abs(got[worst] - ref).max() <= 2.0 * np.abs(want[worst] - ref).max() + 1e-8
 
 
-@pytest.mark.parametrize("N,kernel", [(1024, "Matern32Kernel"), (2048, "OUKernel"), (4096, "OUKernel")])
+@pytest.mark.parametrize("N,kernel", [(1024, "Matern32Kernel"), (2048, "OUKernel"), (4096, "OUKernel"), (6000, "OUKernel")])
 def test_large_n_quasar_like(libgsn, N, kernel):
     """COSMOGRAIL-like long curves (config C3): 1 band x 4 images, OU / Matern-3/2 as in the quasar notebook."""
     from gaussn_b200 import gausSN, kernels, meanfuncs, lensingmodels
     ds = benchdata.make_dataset(N, 1, 4, span=2.0 * (N // 4))
     rng = np.random.default_rng(N)
-    B = 6 if N >= 2048 else 12
+    B = 3 if N > 4096 else 6 if N >= 2048 else 12
     theta = np.column_stack([rng.uniform(0.01, 0.3, B), rng.uniform(50, 400, B), rng.uniform(-0.1, 0.3, B)] +
                             [f(B) for _ in range(3) for f in (lambda b: rng.uniform(0, 60, b), lambda b: rng.uniform(0.3, 1.5, b))])
     gp = gausSN.GP(getattr(kernels, kernel)([0.1, 100.0]), meanfuncs.UniformMean([0.0]),

@@ -169,7 +169,7 @@ def _check_item_order(N, band_of_row, n_bands, masked):
     return items
 
 
-@pytest.mark.parametrize("N", [1, 31, 32, 33, 64, 200, 336, 337, 352, 399, 400, 432, 512, 1000, 2048, 4192])
+@pytest.mark.parametrize("N", [1, 31, 32, 33, 64, 200, 336, 337, 352, 399, 400, 432, 512, 1000, 2048, 4192, 8192])
 def test_item_order_is_complete_and_topological(libgsn, N):
     _check_item_order(N, None, 1, False)
 
