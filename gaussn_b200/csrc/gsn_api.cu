@@ -66,6 +66,7 @@ struct gsn_problem {
   // two launch shapes (see CfgWide / CfgNarrow): the narrow one is available for N <= kNarrowDispatchN and is
   // chosen per call when the batch is large enough to fill the GPU with one-warp CTAs
   bool narrow_ok = false;
+  int64_t narrow_min_batch = 0;   // batches of at least this many thetas use the one-warp shape
   bool tiny_ok = false; int grid_tiny = 0; size_t smem_tiny = 0;   // the one-warp shape at 12 CTAs per SM, N <= 96
   int grid_wide = 0, grid_narrow = 0; size_t smem_wide = 0, smem_narrow = 0;
   // one theta per thread-block cluster, for calls with few thetas (see gsn_cluster.cuh)
@@ -128,7 +129,9 @@ int dispatch_logl_out(gsn_problem* p, const double* theta, int64_t B, int64_t ld
     p->launches += 1;
     return GSN_OK;
   }
-  const bool narrow = p->narrow_ok && B >= gsn::kNarrowMinBatch;
+  int64_t narrow_min = p->narrow_min_batch;
+  if (const char* nm_env = getenv("GSN_NARROW_MIN_BATCH")) narrow_min = atoll(nm_env);   // tuning hook
+  const bool narrow = p->narrow_ok && B >= narrow_min;
   p->last_shape = narrow ? GSN_PATH_DMMA_BLOCKED_NARROW : GSN_PATH_DMMA_BLOCKED;
   const bool tiny = narrow && p->tiny_ok;
   const int grid = (int)std::min<int64_t>(B, tiny ? p->grid_tiny : narrow ? p->grid_narrow : p->grid_wide);
@@ -388,7 +391,11 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   GSN_CUDA_P(cudaMalloc(&p->d_theta_col, sizeof(int) * hcol.size()));
   GSN_CUDA_P(cudaMalloc(&p->d_theta_fixed, sizeof(double) * hfix.size()));
   GSN_CUDA_P(cudaMalloc(&p->d_counter, sizeof(unsigned)));
-  p->narrow_ok = pick_narrow(pd.Npad, effective_order(N, hband, masked));
+  const int64_t n_eff = effective_order(N, hband, masked);
+  p->narrow_ok = pick_narrow(pd.Npad, n_eff);
+  // One warp per theta needs more thetas to pay off the longer its serial chain is (device time per call, one-warp
+  // against four-warp shape: N = 141, B = 500: 124 / 128 us; N = 256, B = 768: 438 / 340 us).
+  p->narrow_min_batch = n_eff <= 224 ? gsn::kNarrowMinBatch : 2 * gsn::kNarrowMinBatch;
   std::vector<unsigned> items = build_item_list(N, hband, masked, p->narrow_ok);
   pd.n_items = (int)items.size();
   {
