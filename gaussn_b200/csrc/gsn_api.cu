@@ -70,7 +70,7 @@ struct gsn_problem {
   bool tiny_ok = false; int grid_tiny = 0; size_t smem_tiny = 0;   // the one-warp shape at 12 CTAs per SM, N <= 96
   int grid_wide = 0, grid_narrow = 0; size_t smem_wide = 0, smem_narrow = 0;
   // one theta per thread-block cluster, for calls with few thetas (see gsn_cluster.cuh)
-  int cluster_cap[4] = {0, 0, 0, 0};   // clusters of 1 << i CTAs (one CTA per SM) the device holds at once
+  int cluster_cap[4] = {0, 0, 0, 0};   // clusters of 1 << i CTAs the device holds at once
   int cluster_max[4] = {0, 0, 0, 0};   // largest batch evaluated one theta per cluster of 1 << i CTAs (0: size not used at this N)
   size_t smem_cluster = 0;
   unsigned* d_items_cluster = nullptr; int n_items_cluster = 0;

@@ -2,7 +2,7 @@
 //
 // The reference's samplers evaluate one parameter vector per call (gaussn/gausSN.py:321-323, :335), and a call with a
 // handful of thetas leaves most of the GPU idle when each theta is confined to one CTA.  Here a thread-block cluster of
-// 2, 4 or 8 four-warp CTAs (chosen per launch), one per SM, works on ONE theta: the same work items, the same dependency-ordered list, the
+// 2, 4 or 8 four-warp CTAs (chosen per launch) works on ONE theta: the same work items, the same dependency-ordered list, the
 // same factor workspace in global memory as gsn::logl_dmma_kernel -- only the control words (dataflow flags done[] / rdy[],
 // the item counter, the failure index, the per-column partial sums) are those of the cluster's rank-0 CTA, which the other
 // CTAs reach through distributed shared memory with cluster-scope acquire / release (Ctl<kCl> in gsn_chol_dmma.cuh).
@@ -31,11 +31,10 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// Shared memory of a cluster CTA; the padding keeps the request above half an SM so that the CTAs of a cluster land on
-// different SMs.
-inline size_t logl_cluster_smem_bytes(int Npad, bool has_aux) {
-  return std::max<size_t>(logl_dmma_smem_bytes<CfgCluster>(Npad, has_aux), (size_t)116 * 1024);
-}
+// Shared memory of a cluster CTA.  (Padding the request above half an SM, to force one CTA per SM, was tried: a lone cluster
+// is spread over SMs anyway, and the padding halves the number of clusters the GPU holds -- B = 100 at N = 1024: 3.0 ms
+// as one CTA per theta, 2.1 ms as 100 two-CTA clusters sharing SMs.)
+inline size_t logl_cluster_smem_bytes(int Npad, bool has_aux) { return logl_dmma_smem_bytes<CfgCluster>(Npad, has_aux); }
 
 template <int KIND>
 __global__ void __launch_bounds__(CfgCluster::kWarps * 32, 1)

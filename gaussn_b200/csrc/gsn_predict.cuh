@@ -95,7 +95,7 @@ inline size_t predict_smem_bytes(int Npad) {
   return b;
 }
 
-inline size_t predict_cluster_smem_bytes(int Npad) { return std::max<size_t>(predict_smem_bytes(Npad), (size_t)116 * 1024); }
+inline size_t predict_cluster_smem_bytes(int Npad) { return predict_smem_bytes(Npad); }
 
 // kCl == 1: one CTA per theta (batches of posterior samples).  kCl > 1: one theta per thread-block cluster, as in
 // gsn_cluster.cuh -- for GP.predict called with a single parameter set on a long light curve.

@@ -104,7 +104,7 @@ typedef enum gsn_query_what {
 typedef enum gsn_path {
   GSN_PATH_DMMA_BLOCKED = 1,        /* four warps per theta (band blocks above 336 rows, or smaller batches): blocked left-looking Cholesky, FP64 DMMA updates, L in a global workspace */
   GSN_PATH_DMMA_BLOCKED_NARROW = 2, /* the same kernel, one warp per theta (largest band block <= 336 rows and B >= 512, or >= 1024 above 224 rows) */
-  GSN_PATH_DMMA_CLUSTER = 3         /* latency-bound calls (N >= 256, at most as many thetas as clusters fit on the GPU): a thread-block cluster of 2, 4 or 8 four-warp CTAs, one per SM, shares one theta */
+  GSN_PATH_DMMA_CLUSTER = 3         /* latency-bound calls (N >= 256, at most as many thetas as clusters fit on the GPU): a thread-block cluster of 2, 4 or 8 four-warp CTAs shares one theta */
 } gsn_path;
 
 /*
