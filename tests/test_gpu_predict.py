@@ -254,3 +254,24 @@ def test_scalar_predict_reuses_handles_across_gp_objects_and_data(libgsn):
         handle = gausSN._PREDICT_HANDLES[(N, _engine.K_EXPSQUARED, _engine.M_UNIFORM, 1, None)][0]
         launches.append(handle.query(_engine.Q_LAUNCHES))
     assert launches == [1, 1, 2, 2, 3, 3]                    # each length kept its handle
+
+
+def test_predict_batch_against_reference_plotting_loop_vectors(libgsn):
+    """gp.predict_batch against outputs of the reference's own code driven as its plotting loop drives it
+    (tests/golden/reference_predict_bands.json, made by tests/golden/make_golden_predict.py)."""
+    import json
+    import os
+    from test_gpu_parity import make_gp
+    here = os.path.dirname(__file__)
+    ref = json.load(open(os.path.join(here, "golden", "reference_predict_bands.json")))
+    base = json.load(open(os.path.join(here, "golden", "reference_vectors.json")))
+    for case in ref["cases"]:
+        ds = base["logl_datasets"][case["dataset"]]
+        nk, nm = gp_oracle.KERNEL_NPARAMS[case["kernel"]], gp_oracle.MEAN_NPARAMS[case["mean"]]
+        th = np.array(case["sample"])
+        gp = make_gp(ds, case["kernel"], th[:nk], case["mean"], th[nk:nk + nm], case["lensing"], th[nk + nm:])
+        gp.bands = np.array(ds["band"])
+        for bi, want in enumerate(case["bands"]):
+            e, v = gp.predict_batch(th[None, :], np.array(case["x_prime"]), band=bi)
+            np.testing.assert_allclose(e[0], want["expectation"], **E_TOL)
+            np.testing.assert_allclose(v[0].ravel(), want["variance"], **V_TOL)

@@ -111,3 +111,25 @@ def test_longdouble_arbiter_agrees_with_oracle(golden):
         ref = ld.loglikelihood_ld(ds["x"], ds["y"], ds["yerr"], row["kernel"], row["kernel_params"], row["mean_params"][0],
                                   row["lensing_params"], nb, ni, idx)
         assert abs(ref - row["logl"]) < 5e-10, (row["dataset"], row["kernel"], ref - row["logl"])
+
+
+def test_predict_per_band_as_the_plotting_loop_does():
+    """The reference's plotting-loop body (utils.py:193-204: lens the band with the sample, divide by the magnifications,
+    GP.predict), run with the reference's own classes by tests/golden/make_golden_predict.py."""
+    import json
+    import os
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_predict_bands.json")))
+    base = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))
+    for case in ref["cases"]:
+        ds = base["logl_datasets"][case["dataset"]]
+        x, y, yerr = (np.array(ds[k]) for k in ("x", "y", "yerr"))
+        idx, nb, ni, _ = _idx(ds)
+        nk, nm = o.KERNEL_NPARAMS[case["kernel"]], o.MEAN_NPARAMS[case["mean"]]
+        th = case["sample"]
+        shifted, b = o.lens(case["lensing"], th[nk + nm:], x, nb, ni, idx)
+        for bi, want in enumerate(case["bands"]):
+            r0, r1 = int(idx[bi * ni]), int(idx[(bi + 1) * ni])
+            e, v = o.predict(case["x_prime"], shifted[r0:r1], y[r0:r1] / b[r0:r1], yerr[r0:r1] / b[r0:r1],
+                             case["kernel"], th[:nk], case["mean"], th[nk:nk + nm])
+            np.testing.assert_allclose(e, want["expectation"], rtol=1e-11, atol=1e-12)
+            np.testing.assert_allclose(v.ravel(), want["variance"], rtol=1e-9, atol=1e-12)
