@@ -207,3 +207,39 @@ def test_predict_item_order_is_complete_and_topological(libgsn, n_rows, M, want_
             if c != j:
                 deps.append((j, j))
         assert all(pos[d] < i for d in deps), ((c, j, trail), deps)
+
+
+def test_long_prediction_grids_are_assembled_from_pairs_of_pieces(monkeypatch):
+    """GP.predict_batch cuts a grid that does not fit one factorisation into pieces and predicts every pair of pieces
+    jointly (the cross blocks of the covariance need both).  Host logic only: the engine call is replaced by an exact
+    numpy conditional, and the assembled moments must equal the direct ones."""
+    from gaussn_b200 import gausSN, _engine
+    rng = np.random.default_rng(5)
+    xv = np.sort(rng.uniform(0, 50, 40))
+    yv = np.sin(xv / 7.0)
+    noise = 0.05
+
+    def k(a, b):
+        return 0.8 * np.exp(-0.5 * (a[:, None] - b[None, :]) ** 2 / 36.0)
+
+    def fake_call(p, th, row0, n_rows, x_prime, mean_v, mean_u, want_cov):
+        C = k(xv, xv) + noise ** 2 * np.eye(len(xv))
+        Kuv = k(np.asarray(x_prime), xv)
+        e = np.tile(Kuv @ np.linalg.solve(C, yv), (th.shape[0], 1))
+        v = np.tile(k(np.asarray(x_prime), np.asarray(x_prime)) - Kuv @ np.linalg.solve(C, Kuv.T), (th.shape[0], 1, 1)) if want_cov else None
+        return e, v
+
+    monkeypatch.setattr(gausSN, "_predict_call", fake_call)
+    th = np.zeros((3, 2))
+    x_prime = np.linspace(-5, 60, 101)
+    e_ref, v_ref = fake_call(None, th, 0, 40, x_prime, None, None, True)
+    monkeypatch.setattr(_engine, "MAX_ORDER", 64 + 30)      # 40 rows pad to 64: room for 30 epochs, pieces of 15
+    e, v = gausSN._predict_chunked(None, th, 0, 40, x_prime, None, None, True)
+    np.testing.assert_allclose(e, e_ref, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(v, v_ref, rtol=0, atol=1e-13)
+    e2, v2 = gausSN._predict_chunked(None, th, 0, 40, x_prime, None, None, False)
+    assert v2 is None
+    np.testing.assert_allclose(e2, e_ref, rtol=0, atol=1e-13)
+    monkeypatch.setattr(_engine, "MAX_ORDER", 64 + 1)
+    with pytest.raises(ValueError):
+        gausSN._predict_chunked(None, th, 0, 40, x_prime, None, None, True)
