@@ -243,3 +243,73 @@ def test_long_prediction_grids_are_assembled_from_pairs_of_pieces(monkeypatch):
     monkeypatch.setattr(_engine, "MAX_ORDER", 64 + 1)
     with pytest.raises(ValueError):
         gausSN._predict_chunked(None, th, 0, 40, x_prime, None, None, True)
+
+
+class _FakeGP:
+    """Stands in for GP in the sampler adapters: a quadratic 'posterior' evaluated in batches, counting the launches."""
+
+    def __init__(self):
+        self.calls = []
+
+    def jointprobability_batch(self, thetas, logprior=None, fix_kernel_params=False, fix_mean_params=False,
+                               fix_lensing_params=False, invert=1):
+        thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+        self.calls.append((thetas.shape[0], (fix_kernel_params, fix_mean_params, fix_lensing_params), invert))
+        val = -0.5 * np.sum((thetas - np.arange(1, thetas.shape[1] + 1)) ** 2, axis=1)
+        if logprior is not None:
+            val = val + np.array([logprior(t) for t in thetas])
+        return invert * val
+
+
+def test_vectorized_posterior_and_batch_pool_evaluate_queues_in_one_call():
+    """the adapters that turn the samplers' one-theta-at-a-time loops (gausSN.py:321-323, :352-359)
+    into batches.  No GPU needed: the likelihood is a stand-in."""
+    from gaussn_b200 import samplers
+    gp = _FakeGP()
+    post = samplers.VectorizedPosterior(gp, lambda t: -0.1 * t[0], False, True, False, invert=1)
+    pts = np.random.default_rng(1).normal(size=(7, 3))
+    out = post(pts)
+    assert out.shape == (7,) and gp.calls[-1] == (7, (False, True, False), 1) and post.n_calls == 1 and post.n_evals == 7
+    one = post(pts[2])
+    assert isinstance(one, float) and one == out[2] and post.n_calls == 2 and post.n_evals == 8
+    # dynesty-style pool: the whole queue in one launch; any other callable falls back to a plain loop
+    pool = samplers.BatchPool(size=64)
+    assert pool.size == 64
+    got = pool.map(post, [p for p in pts])
+    assert np.allclose(got, out) and gp.calls[-1][0] == 7 and post.n_calls == 3
+    assert pool.map(lambda v: v * 2, [1, 2, 3]) == [2, 4, 6]
+
+    def wrapped(theta):          # a function that carries the posterior, as dynesty's loglikelihood wrapper may
+        return post(theta)
+    wrapped.vectorized = post
+    got2 = pool.map(wrapped, [p for p in pts[:4]])
+    assert np.allclose(got2, out[:4]) and gp.calls[-1][0] == 4
+    pool.close(); pool.join()
+
+
+def test_batched_finite_difference_gradient_matches_the_analytic_one():
+    """scipy's minimize differences the scalar objective with P + 1 separate calls (gausSN.py:335); fd_value_and_grad
+    gets value and gradient from one batch of P + 1 points and keeps the steps inside the bounds."""
+    from gaussn_b200 import samplers
+    gp = _FakeGP()
+    post = samplers.VectorizedPosterior(gp, None, False, False, False, invert=-1)     # minimise -logP
+    theta = np.array([0.3, -2.0, 5.0, 40.0])
+    f, g = samplers.fd_value_and_grad(post, theta)
+    assert gp.calls[-1][0] == len(theta) + 1 and post.n_calls == 1
+    want_f = 0.5 * np.sum((theta - np.arange(1, 5)) ** 2)
+    np.testing.assert_allclose(f, want_f, rtol=1e-14)
+    np.testing.assert_allclose(g, theta - np.arange(1, 5), rtol=1e-5, atol=1e-5)   # forward differences: ~eps f / h
+    # a point on its upper bound: the step goes inwards, the gradient is still right
+    bounds = [(0.0, 0.3), (-5.0, 5.0), (None, 5.0), (0.0, None)]
+    f2, g2 = samplers.fd_value_and_grad(post, theta, bounds=bounds)
+    np.testing.assert_allclose(g2, theta - np.arange(1, 5), rtol=1e-5, atol=1e-5)
+    used = None
+
+    class Spy(samplers.VectorizedPosterior):
+        def __call__(self, th):
+            nonlocal used
+            used = np.array(th)
+            return super().__call__(th)
+    spy = Spy(gp, None, False, False, False, invert=-1)
+    samplers.fd_value_and_grad(spy, theta, bounds=bounds)
+    assert np.all(used[1:, 0] <= 0.3) and np.all(used[:, 2] <= 5.0) and np.all(used[:, 3] >= 0.0)
