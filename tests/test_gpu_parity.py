@@ -561,3 +561,25 @@ def test_workspace_grows_with_the_largest_batch(libgsn):
     again = gp.loglikelihood_batch(theta[:1])
     assert gp._problem.query(_engine.Q_WORKSPACE_BYTES) == w3
     assert one[0] == big[0] == again[0] and np.array_equal(mid, big[:200])
+
+
+def test_minimize_finds_the_reference_optimum(libgsn, golden):
+    """optimize_parameters(method='minimize') with the reference's own result as the answer: the optimum that the
+    reference's unmodified optimize_parameters finds on the same data with the same Nelder-Mead settings
+    (tests/golden/make_golden_minimize.py).  Pins the whole drop-in call: index bookkeeping, theta packing, invert = -1."""
+    import json
+    import os
+    from gaussn_b200 import gausSN, kernels, meanfuncs, lensingmodels
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_minimize.json")))
+    for case in ref["cases"]:
+        ds = golden["logl_datasets"][case["dataset"]]
+        gp = gausSN.GP(kernels.ExpSquaredKernel(list(case["kernel0"])), meanfuncs.UniformMean(list(case["mean0"])),
+                       lensingmodels.ConstantMagnification(list(case["lens0"])))
+        res = gp.optimize_parameters(np.array(ds["x"]), np.array(ds["y"]), np.array(ds["yerr"]), band=np.array(ds["band"]),
+                                     image=np.array(ds["image"]), method="minimize", fix_mean_params=case["fix_mean"],
+                                     minimize_kwargs=case["minimize_kwargs"])
+        assert res.success
+        # the simplex walks on function values that agree to ~1e-10, so the two runs may part ways late: same optimum,
+        # not the same iterates
+        assert abs(res.fun - case["fun"]) <= 1e-8, (res.fun, case["fun"])
+        np.testing.assert_allclose(res.x, case["x"], rtol=1e-5, atol=1e-5)
