@@ -21,10 +21,11 @@ HEADERS = [
     os.path.join(CSRC, "gsn_launch.h"),
     os.path.join(CSRC, "gsn_predict.cuh"),
     os.path.join(CSRC, "gsn_cluster.cuh"),
+    os.path.join(CSRC, "gsn_onchip.cuh"),
     os.path.join(REPO_DIR, "include", "gsn.h"),
 ]
 SOURCES = [os.path.join(CSRC, "gsn_api.cu"), os.path.join(CSRC, "gsn_kernels.cu"), os.path.join(CSRC, "gsn_predict.cu"),
-           os.path.join(CSRC, "gsn_cluster.cu")]
+           os.path.join(CSRC, "gsn_cluster.cu"), os.path.join(CSRC, "gsn_onchip.cu")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -46,6 +47,8 @@ UNITS = [
     ("gsn_tiny_b", "gsn_kernels.cu", ["-DGSN_SLICE_CFG=CfgTiny", "-DGSN_SLICE_NAME=launch_logl_tiny_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
     ("gsn_cluster_a", "gsn_cluster.cu", ["-DGSN_SLICE_NAME=launch_logl_cluster_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),
     ("gsn_cluster_b", "gsn_cluster.cu", ["-DGSN_SLICE_NAME=launch_logl_cluster_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
+    ("gsn_onchip_a", "gsn_onchip.cu", ["-DGSN_SLICE_NAME=launch_logl_onchip_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),
+    ("gsn_onchip_b", "gsn_onchip.cu", ["-DGSN_SLICE_NAME=launch_logl_onchip_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
     ("gsn_predict_a", "gsn_predict.cu", ["-DGSN_SLICE_NAME=launch_predict_a", "-DGSN_SLICE_LO=0", "-DGSN_SLICE_HI=4"]),
     ("gsn_predict_b", "gsn_predict.cu", ["-DGSN_SLICE_NAME=launch_predict_b", "-DGSN_SLICE_LO=5", "-DGSN_SLICE_HI=10"]),
 ]

@@ -74,7 +74,15 @@ struct gsn_problem {
   int cluster_max[4] = {0, 0, 0, 0};   // largest batch evaluated one theta per cluster of 1 << i CTAs (0: size not used at this N)
   size_t smem_cluster = 0;
   unsigned* d_items_cluster = nullptr; int n_items_cluster = 0;
+  // factor resident in shared memory (gsn_onchip.cuh): band blocks of at most kOnchipMaxTiles tile rows
+  bool onchip_ok = false;
+  gsn::OnchipDev od{};
+  int4* d_oc_blk = nullptr; double* d_oc_x = nullptr; double* d_oc_y = nullptr; double* d_oc_yerr2 = nullptr;
+  int* d_oc_img = nullptr; int* d_oc_urow = nullptr;
+  std::vector<int> h_oc_urow;
+  size_t smem_onchip = 0; int onchip_ctas_smem = 0, onchip_regs = 0;
   int last_shape = 0;
+  int last_warps = 0;     // warps per theta of the most recent on-chip launch
   int n_theta_cols = 0;   // columns the caller's theta must provide
   // host staging for gsn_logl_batch_host
   double* h_theta = nullptr; double* h_logl = nullptr; int* h_info = nullptr;
@@ -112,6 +120,29 @@ int dispatch_logl_out(gsn_problem* p, const double* theta, int64_t B, int64_t ld
   // (and single calls, which is how the reference's samplers use the likelihood) four warps per theta give the
   // lower latency (N = 141: 96 us against 161 us per call; B = 4096: 1.04 ms against 1.33 ms the other way round).
   const int k = p->kernel_kind;
+  if (p->onchip_ok) {
+    // Small band blocks: the factor never leaves the SM.  T warps share one theta; T is the smallest team that fills an SM
+    // with warps given how many thetas its shared memory holds, and larger for calls with too few thetas to fill the GPU.
+    // Results do not depend on T (same tile arithmetic, whoever runs it).
+    const int warps_max = std::max(1, std::min(64, 65536 / (((p->onchip_regs + 7) / 8 * 8) * 32)));
+    int target = 16;
+    if (const char* e = getenv("GSN_ONCHIP_WARPS_PER_SM")) target = std::max(1, atoi(e));
+    int t_cap = 1;
+    while (t_cap < gsn::kOnchipMaxWarps && 2 * t_cap <= p->od.nt_max) t_cap *= 2;   // a team larger than the tile rows idles
+    int T = 1;
+    while (T < t_cap && T * p->onchip_ctas_smem < target) T *= 2;
+    while (T < t_cap && B * T * 2 <= (int64_t)p->sm_count * 4) T *= 2;               // few thetas: shorter critical path per theta
+    if (const char* e = getenv("GSN_ONCHIP_T")) T = std::max(1, std::min(gsn::kOnchipMaxWarps, atoi(e)));
+    const int ctas = std::max(1, std::min(std::min(p->onchip_ctas_smem, 32), warps_max / T));
+    const int grid = (int)std::min<int64_t>(B, (int64_t)p->sm_count * ctas);
+    p->last_shape = GSN_PATH_ONCHIP;
+    p->last_warps = T;
+    gsn::OnchipLaunchArgs a{p->pd, p->od, theta, B, ld, hostmean, out, info, flags, p->d_counter, grid, T, p->smem_onchip, stream};
+    const cudaError_t e = (k <= 4) ? gsn::launch_logl_onchip_a(k, &a, nullptr) : gsn::launch_logl_onchip_b(k, &a, nullptr);
+    if (e != cudaSuccess) return fail(GSN_ERR_CUDA, "on-chip log-likelihood kernel launch failed: %s", cudaGetErrorString(e));
+    p->launches += 1;
+    return GSN_OK;
+  }
   int cl = 0;   // log2 of the cluster size: the largest whose clusters hold all thetas of the call at once
   for (int i = 3; i >= 1 && !cl; --i)
     if (B <= p->cluster_max[i]) cl = i;
@@ -271,12 +302,19 @@ std::vector<unsigned> build_item_list(int64_t N, const std::vector<int>& band_in
   return items;
 }
 
+// GSN_FORCE_SHAPE = narrow | wide | cluster2 | cluster4 | cluster8 forces one of the workspace shapes (tests, tuning);
+// "legacy" only switches the on-chip shape off and leaves the dispatch among the workspace shapes as it is.
+const char* forced_shape() {
+  const char* e = getenv("GSN_FORCE_SHAPE");
+  return (e && e[0] != 'l') ? e : nullptr;
+}
+
 bool pick_narrow(int64_t N, int64_t n_eff) {
   // one warp per theta while a theta has short item chains (see CfgNarrow): judged by the largest band block when a
   // band mask splits the factorisation (4 bands x 128 rows behaves like N = 128, not 512); GSN_FORCE_SHAPE=narrow|wide
   // is a tuning hook
   bool narrow = n_eff <= gsn::kNarrowDispatchN && N <= gsn::kNarrowMaxN;
-  if (const char* shape_env = getenv("GSN_FORCE_SHAPE")) narrow = (shape_env[0] == 'n') && N <= gsn::kNarrowMaxN;
+  if (const char* shape_env = forced_shape()) narrow = (shape_env[0] == 'n') && N <= gsn::kNarrowMaxN;
   return narrow;
 }
 
@@ -449,7 +487,7 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
   // cluster shape: cluster sizes whose warps the order can feed.  GSN_FORCE_SHAPE=cluster2|cluster4|cluster8 forces one
   // size at any order (tests); wide / narrow switch the shape off.
   {
-    const char* shape_env = getenv("GSN_FORCE_SHAPE");
+    const char* shape_env = forced_shape();
     p->smem_cluster = gsn::logl_cluster_smem_bytes(pd.Npad, has_aux);
     bool any = false;
     for (int i = 1; i <= 3 && p->smem_cluster <= 226 * 1024; ++i) {
@@ -471,6 +509,60 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
       GSN_CUDA_P(cudaMemcpy(p->d_items_cluster, citems.data(), sizeof(unsigned) * citems.size(), cudaMemcpyHostToDevice));
     }
   }
+  // on-chip shape: every band block (the whole matrix without a band mask) in at most kOnchipMaxTiles tile rows
+  {
+    std::vector<int4> blk;
+    std::vector<int> urow;
+    int nt_max = 0, groups = 0;
+    int64_t b0 = 0;
+    while (b0 < N) {
+      int64_t b1 = N;
+      if (masked) { b1 = b0; while (b1 < N && uband[b1] == uband[b0]) ++b1; }
+      const int rows = (int)(b1 - b0), nt = (rows + 7) / 8;
+      blk.push_back(make_int4((int)urow.size(), nt, groups, rows));
+      for (int64_t u = b0; u < b1; ++u) urow.push_back((int)u);
+      while (urow.size() % 8) urow.push_back(-1);
+      nt_max = std::max(nt_max, nt);
+      groups += (nt + 3) / 4;
+      b0 = b1;
+    }
+    int max_rows = 8 * gsn::kOnchipMaxTiles;
+    if (const char* e = getenv("GSN_ONCHIP_MAX_ROWS")) max_rows = atoi(e);   // tuning hook; 0 switches the shape off
+    const char* shape_env = getenv("GSN_FORCE_SHAPE");                       // any forced legacy shape switches it off as well
+    const gsn::OnchipSmem lay(nt_max, groups, pd.P, has_aux);
+    if (!shape_env && nt_max <= gsn::kOnchipMaxTiles && 8 * nt_max <= max_rows + 7 && (int)blk.size() <= gsn::kOnchipMaxBlocks &&
+        lay.bytes <= 226 * 1024) {
+      const size_t nr = urow.size();
+      std::vector<double> ox(nr, 0.0), oy(nr, 0.0), oe(nr, 1.0);
+      std::vector<int> oimg(nr, 0);
+      for (size_t i = 0; i < nr; ++i) {
+        const int u = urow[i];
+        if (u < 0) continue;
+        ox[i] = x[u]; oy[i] = y[u]; oe[i] = yerr[u] * yerr[u]; oimg[i] = uimg[u];
+      }
+      GSN_CUDA_P(cudaMalloc(&p->d_oc_blk, sizeof(int4) * blk.size()));
+      GSN_CUDA_P(cudaMalloc(&p->d_oc_x, sizeof(double) * nr));
+      GSN_CUDA_P(cudaMalloc(&p->d_oc_y, sizeof(double) * nr));
+      GSN_CUDA_P(cudaMalloc(&p->d_oc_yerr2, sizeof(double) * nr));
+      GSN_CUDA_P(cudaMalloc(&p->d_oc_img, sizeof(int) * nr));
+      GSN_CUDA_P(cudaMalloc(&p->d_oc_urow, sizeof(int) * nr));
+      GSN_CUDA_P(cudaMemcpy(p->d_oc_blk, blk.data(), sizeof(int4) * blk.size(), cudaMemcpyHostToDevice));
+      GSN_CUDA_P(cudaMemcpy(p->d_oc_x, ox.data(), sizeof(double) * nr, cudaMemcpyHostToDevice));
+      GSN_CUDA_P(cudaMemcpy(p->d_oc_y, oy.data(), sizeof(double) * nr, cudaMemcpyHostToDevice));
+      GSN_CUDA_P(cudaMemcpy(p->d_oc_yerr2, oe.data(), sizeof(double) * nr, cudaMemcpyHostToDevice));
+      GSN_CUDA_P(cudaMemcpy(p->d_oc_img, oimg.data(), sizeof(int) * nr, cudaMemcpyHostToDevice));
+      GSN_CUDA_P(cudaMemcpy(p->d_oc_urow, urow.data(), sizeof(int) * nr, cudaMemcpyHostToDevice));
+      p->od.n_blocks = (int)blk.size(); p->od.nt_max = nt_max; p->od.n_groups = groups;
+      p->od.blk = p->d_oc_blk; p->od.x = p->d_oc_x; p->od.y = p->d_oc_y; p->od.yerr2 = p->d_oc_yerr2;
+      p->od.img = p->d_oc_img; p->od.urow = p->d_oc_urow;
+      p->h_oc_urow = urow;
+      p->smem_onchip = lay.bytes;
+      p->onchip_ctas_smem = std::max(1, (int)((size_t)(227 * 1024) / (lay.bytes + 1024)));
+      GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_onchip_a(kernel_kind, nullptr, &p->onchip_regs)
+                                    : gsn::launch_logl_onchip_b(kernel_kind, nullptr, &p->onchip_regs));
+      p->onchip_ok = true;
+    }
+  }
   GSN_CUDA_P(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
 #undef GSN_CUDA_P
   *out = p;
@@ -484,6 +576,7 @@ int gsn_problem_destroy(gsn_problem* p) {
   cudaFree(p->d_theta_col); cudaFree(p->d_theta_fixed); cudaFree(p->d_workspace); cudaFree(p->d_counter); cudaFree(p->d_items); cudaFree(p->d_items_cluster);
   cudaFree(p->d_theta); cudaFree(p->d_logl); cudaFree(p->d_info);
   cudaFree(p->d_pred_ws); cudaFree(p->d_pred_items);
+  cudaFree(p->d_oc_blk); cudaFree(p->d_oc_x); cudaFree(p->d_oc_y); cudaFree(p->d_oc_yerr2); cudaFree(p->d_oc_img); cudaFree(p->d_oc_urow);
   if (p->h_theta) cudaFreeHost(p->h_theta);
   if (p->h_logl) cudaFreeHost(p->h_logl);
   if (p->h_info) cudaFreeHost(p->h_info);
@@ -507,6 +600,17 @@ int gsn_problem_set_data(gsn_problem* p, const double* x, const double* y, const
   GSN_CUDA(cudaMemcpy(p->d_x, hx.data(), nb, cudaMemcpyHostToDevice));
   GSN_CUDA(cudaMemcpy(p->d_y, hy.data(), nb, cudaMemcpyHostToDevice));
   GSN_CUDA(cudaMemcpy(p->d_yerr2, he.data(), nb, cudaMemcpyHostToDevice));
+  if (p->onchip_ok) {
+    const size_t nr = p->h_oc_urow.size();
+    std::vector<double> ox(nr, 0.0), oy(nr, 0.0), oe(nr, 1.0);
+    for (size_t i = 0; i < nr; ++i) {
+      const int u = p->h_oc_urow[i];
+      if (u >= 0) { ox[i] = x[u]; oy[i] = y[u]; oe[i] = yerr[u] * yerr[u]; }
+    }
+    GSN_CUDA(cudaMemcpy(p->d_oc_x, ox.data(), sizeof(double) * nr, cudaMemcpyHostToDevice));
+    GSN_CUDA(cudaMemcpy(p->d_oc_y, oy.data(), sizeof(double) * nr, cudaMemcpyHostToDevice));
+    GSN_CUDA(cudaMemcpy(p->d_oc_yerr2, oe.data(), sizeof(double) * nr, cudaMemcpyHostToDevice));
+  }
   return GSN_OK;
 }
 
@@ -662,7 +766,7 @@ int gsn_predict_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_
   // a call with few parameter sets (GP.predict: one) on a long light curve: one theta per thread-block cluster
   int cl = 0;
   {
-    const char* shape_env = getenv("GSN_FORCE_SHAPE");
+    const char* shape_env = forced_shape();
     for (int i = 3; i >= 1 && !cl; --i) {
       bool want = pa.Npad >= gsn::kClusterMinN[i];
       if (shape_env) want = shape_env[0] == 'c' && atoi(shape_env + 7) == (1 << i);
@@ -779,6 +883,9 @@ int64_t gsn_query(const gsn_problem* p, int32_t what) {
     case GSN_Q_CLUSTER2_MAX: return p->cluster_max[1];
     case GSN_Q_CLUSTER4_MAX: return p->cluster_max[2];
     case GSN_Q_CLUSTER8_MAX: return p->cluster_max[3];
+    case GSN_Q_ONCHIP: return p->onchip_ok ? 1 : 0;
+    case GSN_Q_ONCHIP_WARPS: return p->last_warps;
+    case GSN_Q_ONCHIP_SMEM: return (int64_t)p->smem_onchip;
   }
   return -1;
 }

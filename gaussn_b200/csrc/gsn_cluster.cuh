@@ -75,7 +75,7 @@ logl_cluster_kernel(ProblemDev pd, const double* __restrict__ theta, long long B
         for (int jj = 0; jj < nblk; ++jj) { zsum += sh.zzj[jj]; ldsum += sh.ldj[jj]; }
         double ll = -0.5 * (pd.nlog2pi + ldsum + zsum);
         int inf = 0;
-        if (sh.fail != 0) { ll = nan(""); inf = sh.fail; }
+        if (sh.fail != 0) { ll = nan(""); inf = failed_row(pd, sh.fail); }
         else if (!isfinite(ll)) inf = -1;
         if ((flags & GSN_FLAG_NEG_INF) && !isfinite(ll)) ll = -INFINITY;
         for (int r = 0; r < out.n; ++r) out.ptr[r][out.offset + prev] = ll;

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include "gsn_chol_dmma.cuh"
 #include "gsn_predict.cuh"
+#include "gsn_onchip.cuh"
 
 namespace gsn {
 
@@ -38,6 +39,26 @@ cudaError_t launch_logl_tiny_b(int kind, const LaunchArgs* a);
 // a == nullptr prepares the kernel and reports how many clusters of `cluster` CTAs can be resident at once.
 cudaError_t launch_logl_cluster_a(int kind, const LaunchArgs* a, size_t smem, int cluster, int* max_clusters);   // kinds 0..4
 cudaError_t launch_logl_cluster_b(int kind, const LaunchArgs* a, size_t smem, int cluster, int* max_clusters);   // kinds 5..10
+
+// Factor resident in shared memory (gsn_onchip.cuh): band blocks of at most kOnchipMaxTiles tile rows.
+struct OnchipLaunchArgs {
+  ProblemDev pd;
+  OnchipDev od;
+  const double* theta;
+  long long B, ld;
+  const double* hostmean;
+  GatherOut out;
+  int* info;
+  unsigned flags;
+  unsigned* counter;
+  int grid;
+  int warps;          // warps per theta (= CTA size / 32): 1, 2, 4, 8 or 16
+  size_t smem_bytes;
+  cudaStream_t stream;
+};
+// a == nullptr prepares the kernel and reports its register count.
+cudaError_t launch_logl_onchip_a(int kind, const OnchipLaunchArgs* a, int* regs);   // kinds 0..4
+cudaError_t launch_logl_onchip_b(int kind, const OnchipLaunchArgs* a, int* regs);   // kinds 5..10
 
 struct PredictLaunchArgs {
   ProblemDev pd;

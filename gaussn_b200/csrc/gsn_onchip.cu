@@ -1,0 +1,49 @@
+// Instantiations of gsn::logl_onchip_kernel (factor resident in shared memory, small band blocks).  Compiled twice with
+//   -DGSN_SLICE_NAME=... -DGSN_SLICE_LO=.. -DGSN_SLICE_HI=..      (see gaussn_b200/build.py)
+#include "gsn_launch.h"
+#include "gsn_onchip.cuh"
+
+namespace gsn {
+
+template <int KIND>
+static cudaError_t prepare_one(int* regs) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (!attr_set[dev & 63]) {
+    e = cudaFuncSetAttribute(logl_onchip_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  if (regs) {
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, logl_onchip_kernel<KIND>);
+    if (e != cudaSuccess) return e;
+    *regs = fa.numRegs;
+  }
+  return cudaSuccess;
+}
+
+template <int KIND>
+static cudaError_t launch_one(const OnchipLaunchArgs& a) {
+  cudaError_t e = prepare_one<KIND>(nullptr);
+  if (e != cudaSuccess) return e;
+  logl_onchip_kernel<KIND><<<a.grid, a.warps * 32, a.smem_bytes, a.stream>>>(a.pd, a.od, a.theta, a.B, a.ld, a.hostmean, a.out, a.info,
+                                                                             a.flags, a.counter);
+  return cudaGetLastError();
+}
+
+template <int KIND>
+static cudaError_t dispatch(int kind, const OnchipLaunchArgs* a, int* regs) {   // a == nullptr: prepare only
+  if constexpr (KIND > GSN_SLICE_HI) {
+    return cudaErrorInvalidValue;
+  } else {
+    if (kind == KIND) return a ? launch_one<KIND>(*a) : prepare_one<KIND>(regs);
+    return dispatch<KIND + 1>(kind, a, regs);
+  }
+}
+
+cudaError_t GSN_SLICE_NAME(int kind, const OnchipLaunchArgs* a, int* regs) { return dispatch<GSN_SLICE_LO>(kind, a, regs); }
+
+}  // namespace gsn

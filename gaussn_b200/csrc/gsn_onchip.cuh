@@ -1,0 +1,398 @@
+// Small band blocks: the log-likelihood with the Cholesky factor resident in shared memory.
+//
+// The reference's own data sets are small: N = 141 (ipynb/fitting_glQSO_example.ipynb), N = 194 in four band blocks of
+// about 48 rows (ipynb/fitting_SLSN_example.ipynb), and with a lensing model the covariance -- so its factor -- is block
+// diagonal by band (lensingmodels.py:39-51).  For such blocks (up to 224 rows) the factor of one band block
+// fits the shared memory of an SM, and this kernel keeps it there: nothing of size N^2 touches global memory, the only
+// HBM traffic of an evaluation is theta in and logL out.
+//
+// Replaces gaussn/gausSN.py:135-160 (GP.loglikelihood) exactly as gsn::logl_dmma_kernel does, with the same per-tile
+// arithmetic in the same order -- results are bit-identical to that kernel (tests/test_gpu_onchip.py) -- but at 8-row
+// granularity (N = 141 is factored as 144 rows, not 160) and without workspace, cp.async rings or item lists.
+//
+// Layout.  The rows of every band block start at a multiple of 8 (`OnchipDev`; padding rows are identity rows).  A block
+// of nt tile rows is stored as packed lower-triangular 8x8 tiles, tile (i, k) at i(i+1)/2 + k, each tile in the universal
+// layout of gsn_chol_dmma.cuh (lane t owns the 16 bytes at offset 2t doubles: conflict-free 512-byte warp accesses, and a
+// lane only ever touches its own 16 bytes of a tile).  The diagonal slot (j, j) holds -inv(L(j, j)): the diagonal tile
+// itself is never read again once its inverse exists.
+//
+// Schedule.  A team of T warps (T = blockDim.x / 32 = 1, 2, 4, 8 or 16, chosen by the host so that an SM holds 16 warps)
+// factors one theta; tile row i belongs to warp i mod T.  Left-looking by tile columns:
+//     T(i, j), i > j:  S = sum_{k<j} L(i,k) L(j,k)^T - K(i,j);  L(i,j) = -S inv(L(j,j))^T         (2j + 2 DMMA)
+//     D(j):            S = sum_{k<j} L(j,k) L(j,k)^T - K(j,j), 8x8 Cholesky + inverse by the warp; the residual b m(x~) - y
+//                      rides along as row 0 of an extra tile Z, whose "L" is z^T = (L^-1 r)^T
+// A warp sweeps the columns; in column j it first runs T(j+1, j) and D(j+1) back to back if row j+1 is its own
+// (look-ahead: the next column's pivot tile is on the critical path), then its other rows two at a time (two independent
+// accumulator chains per B operand).  Row operands L(i, k) are the warp's own stores; the only cross-warp data are row j
+// (needed from column j on) and -inv(L(j,j)), z(j).  Two monotone counters in shared memory carry that dataflow:
+// prog_row (rows complete up to their last off-diagonal tile), prog_diag (pivot tiles factored) and prog_z (z stored),
+// release / acquire at CTA scope; the GEMM of T(i, j) only needs prog_row > j, so it overlaps the 8x8 factorisation of D(j)
+// and waits for prog_diag > j just before its solve; z is only read by the pivot rows, off the critical path.  Every wait is on work that precedes the waiter in column order: no deadlock.
+// With T = 1 there is no flag traffic at all.
+//
+// logL = -1/2 (N ln 2pi + sum ln pivots + z^T z), reduced per 32-row group in a fixed order.
+#pragma once
+#include "gsn_chol_dmma.cuh"
+
+namespace gsn {
+
+constexpr int kOnchipMaxTiles = 28;    // largest band block: 224 rows (406 tiles = 203 KB)
+constexpr int kOnchipMaxWarps = 16;
+constexpr int kOnchipMaxBlocks = 256;
+
+struct OnchipDev {
+  int n_blocks;        // band blocks (1 without a band mask)
+  int nt_max;          // tile rows of the largest block
+  int n_groups;        // 32-row groups over all blocks: granularity of the final reduction
+  const int4* blk;     // [n_blocks] {first row in the on-chip layout, tile rows, first group, real rows}
+  const double* x;     // per row of the on-chip layout (bands aligned to 8 rows)
+  const double* y;
+  const double* yerr2;
+  const int* img;
+  const int* urow;     // caller's row, -1 for padding rows
+};
+
+struct OnchipCtl {
+  int fail;            // 0, or 1-based caller's row of the first non-positive pivot
+  int next;            // theta index taken by the CTA
+  int prog_row;        // rows [0, prog_row) are stored through their last off-diagonal tile
+  int prog_diag;       // pivot tiles [0, prog_diag) are factored: -inv(L(j,j)) is stored
+  int prog_z;          // z(0) ... z(prog_z - 1) are stored
+  double gmant[8];     // pivot product of each 32-row group of the block in work, as mantissa ...
+  int gexpo[8];        // ... and exponent; the logarithms are taken after the factorisation, off its critical path
+};
+
+// Shared-memory carve-up (offsets in doubles).
+struct OnchipSmem {
+  int off_theta, off_ldg, off_zzg, off_ctl, off_vec, off_tiles, vstride;
+  size_t bytes;
+  __host__ __device__ OnchipSmem(int nt_max, int n_groups, int P, bool has_aux) {
+    int o = 64;                                   // 2^(j/64) table of fast_exp
+    off_theta = o; o += (P + 1) & ~1;
+    off_ldg = o; o += n_groups;
+    off_zzg = o; o += n_groups;
+    o = (o + 1) & ~1;
+    off_ctl = o; o += (int)((sizeof(OnchipCtl) + 15) / 16 * 2);   // vectors and tiles are accessed 16 bytes at a time
+    vstride = 8 * nt_max;
+    off_vec = o; o += vstride * (has_aux ? 6 : 5);   // shifted epochs, magnifications, residual, yerr^2, z, [aux]
+    off_tiles = o; o += nt_max * (nt_max + 1) / 2 * 64;
+    bytes = (size_t)o * 8;
+  }
+};
+
+__device__ __forceinline__ bool onchip_wait_gt(const int* p, int v, const int* fail) {
+  while (ld_acquire_shared(p) <= v) {
+    if (ld_volatile_shared(fail) != 0) return false;
+    __nanosleep(20);
+  }
+  return true;
+}
+
+template <int KIND>
+struct OnchipTeam {
+  KernelConsts kc;
+  const double* exptab;
+  const double *xs, *bs, *rs, *e2, *aux;
+  double* zs;
+  double2* tiles;      // already offset by lane
+  OnchipCtl* ctl;
+  double* ldg;
+  const int* urow;     // of this block
+  int lane, T, nt, nrows, n_total;
+
+  struct Cols { double2 x, ba, a; };   // per-lane column data of a tile column: epochs, magnification * amplitude, auxiliary
+
+  __device__ __forceinline__ Cols load_cols(int j) const {
+    const int c = 8 * j + (lane & 3) * 2;
+    Cols q;
+    q.x = *reinterpret_cast<const double2*>(xs + c);
+    const double2 b = *reinterpret_cast<const double2*>(bs + c);
+    q.ba = make_double2(b.x * kc.amp, b.y * kc.amp);      // gausSN.py:146 with the kernel's leading factor folded in
+    q.a = kernel_has_aux<KIND>() ? *reinterpret_cast<const double2*>(aux + c) : make_double2(0.0, 0.0);
+    return q;
+  }
+
+  // -K(i, j) for one tile: shifted epochs, magnifications, noise diagonal (gausSN.py:146-147), identity on padding rows.
+  __device__ __forceinline__ double2 build(int i, int j, const Cols& q) const {
+    const int row = 8 * i + (lane >> 2), col = 8 * j + (lane & 3) * 2;
+    const double xr = xs[row], nbr = -bs[row];
+    const double ar = kernel_has_aux<KIND>() ? aux[row] : 0.0;
+    double2 v;
+    v.x = (nbr * q.ba.x) * cov_unit_sym<KIND>(kc, xr, q.x.x, ar, q.a.x, exptab);
+    v.y = (nbr * q.ba.y) * cov_unit_sym<KIND>(kc, xr, q.x.y, ar, q.a.y, exptab);
+    if (i == j) {
+      if (row == col) v.x -= e2[row];
+      if (row == col + 1) v.y -= e2[row];
+    }
+    if (i == nt - 1) {   // the block's last tile row may carry padding rows (and, on the diagonal tile, padding columns)
+      if (row >= nrows || col >= nrows) v.x = (row == col) ? -1.0 : 0.0;
+      if (row >= nrows || col + 1 >= nrows) v.y = (row == col + 1) ? -1.0 : 0.0;
+    }
+    return v;
+  }
+
+  __device__ __forceinline__ static int tri(int i) { return i * (i + 1) / 2; }
+  __device__ __forceinline__ double2 zfrag(int k) const {   // z(k) as row 0 of an operand tile
+    return (lane < 4) ? *reinterpret_cast<const double2*>(zs + 8 * k + 2 * lane) : make_double2(0.0, 0.0);
+  }
+
+  // Column j for R of this warp's rows: T(i[r], j).  Returns false if the theta failed while waiting.
+  template <int R>
+  __device__ __forceinline__ bool panel(const int (&i)[R], int j, const Cols& q, bool& row_ok, bool& diag_ok) const {
+    double2 S[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) S[r] = build(i[r], j, q);
+    if (T > 1 && !row_ok) {
+      if (!onchip_wait_gt(&ctl->prog_row, j, &ctl->fail)) return false;
+      row_ok = true;
+    }
+    const double2* Bp = tiles + tri(j) * 32;
+    const double2* Ap[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) Ap[r] = tiles + tri(i[r]) * 32;
+#pragma unroll 2
+    for (int k = 0; k < j; ++k) {
+      const double2 b = Bp[k * 32];
+      double2 a[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) a[r] = Ap[r][k * 32];
+#pragma unroll
+      for (int r = 0; r < R; ++r) dmma(S[r], a[r].x, b.x);
+#pragma unroll
+      for (int r = 0; r < R; ++r) dmma(S[r], a[r].y, b.y);
+    }
+    if (T > 1 && !diag_ok) {
+      if (!onchip_wait_gt(&ctl->prog_diag, j, &ctl->fail)) return false;
+      diag_ok = true;
+    }
+    const double2 nW = Bp[j * 32];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double2 X = make_double2(0.0, 0.0);
+      dmma(X, S[r].x, nW.x);
+      dmma(X, S[r].y, nW.y);
+      const_cast<double2*>(Ap[r])[j * 32] = X;
+    }
+    return true;
+  }
+
+  // Look-ahead: T(i, j) for i = j + 1 (skipped for j = -1) and D(i) back to back.
+  // Critical path of the whole factorisation: prog_diag > j  ->  solve  ->  D += X X^T  ->  8x8 elimination  ->  prog_diag = i + 1.
+  // Everything else (the GEMMs over k < j, the residual row Z, the pivot products) is kept off it.
+  __device__ __forceinline__ bool pivot_row(int j) const {
+    const int i = j + 1;
+    const Cols qi = load_cols(i);
+    double2 S = make_double2(0.0, 0.0), X = make_double2(0.0, 0.0);
+    double2 D = build(i, i, qi);
+    double2 Z = make_double2(0.0, 0.0);
+    if (lane < 4) {
+      const double2 r2 = *reinterpret_cast<const double2*>(rs + 8 * i + 2 * lane);
+      Z = make_double2(-r2.x, -r2.y);
+    }
+    double2* Ap = tiles + tri(i) * 32;
+    if (j >= 0) {
+      S = build(i, j, load_cols(j));
+      if (T > 1 && !(onchip_wait_gt(&ctl->prog_row, j, &ctl->fail) && onchip_wait_gt(&ctl->prog_z, j - 1, &ctl->fail))) return false;
+      const double2* Bp = tiles + tri(j) * 32;
+#pragma unroll 2
+      for (int k = 0; k < j; ++k) {
+        const double2 b = Bp[k * 32];
+        const double2 a = Ap[k * 32];
+        const double2 z = zfrag(k);
+        dmma(S, a.x, b.x);
+        dmma(D, a.x, a.x);
+        dmma(Z, z.x, a.x);
+        dmma(S, a.y, b.y);
+        dmma(D, a.y, a.y);
+        dmma(Z, z.y, a.y);
+      }
+      if (T > 1 && !onchip_wait_gt(&ctl->prog_diag, j, &ctl->fail)) return false;
+      const double2 nWj = Bp[j * 32];
+      dmma(X, S.x, nWj.x);
+      dmma(X, S.y, nWj.y);
+      Ap[j * 32] = X;
+      if (T > 1) {
+        __syncwarp();
+        if (lane == 0) st_release_shared(&ctl->prog_row, i + 1);
+      }
+      dmma(D, X.x, X.x);
+      dmma(D, X.y, X.y);
+    }
+    double mant = 1.0;
+    int expo = 0, failrow = -1;
+    double2 nW;
+    chol8_inv_warp(make_double2(-D.x, -D.y), lane, nW, mant, expo, failrow);
+    Ap[i * 32] = nW;
+    if (T > 1) {
+      __syncwarp();
+      if (lane == 0) st_release_shared(&ctl->prog_diag, i + 1);
+    }
+    // ---- off the critical path: the residual row, the pivot product, the failure index
+    if (j >= 0) {
+      if (T > 1 && !onchip_wait_gt(&ctl->prog_z, j, &ctl->fail)) return false;
+      const double2 z = zfrag(j);
+      dmma(Z, z.x, X.x);
+      dmma(Z, z.y, X.y);
+    }
+    double2 Zf = make_double2(0.0, 0.0);
+    dmma(Zf, Z.x, nW.x);
+    dmma(Zf, Z.y, nW.y);
+    if (lane < 4) *reinterpret_cast<double2*>(zs + 8 * i + 2 * lane) = Zf;
+    if (lane == 0) {
+      if (failrow >= 0) {   // a padding row can only get here through NaNs that an earlier row produced
+        const int u = urow[8 * i + failrow];
+        atomicCAS(&ctl->fail, 0, u >= 0 ? u + 1 : n_total);
+      }
+      // running pivot product of the 32-row group: continues where D(i - 1) left it (pivot rows run in order)
+      if ((i & 3) != 0) { mant *= ctl->gmant[i >> 2]; expo += ctl->gexpo[i >> 2]; }
+      ctl->gmant[i >> 2] = mant;
+      ctl->gexpo[i >> 2] = expo;
+    }
+    __syncwarp();
+    if (T > 1 && lane == 0) st_release_shared(&ctl->prog_z, i + 1);
+    return true;
+  }
+
+  __device__ __forceinline__ void factor(int warp) const {
+    for (int j = -1; j < nt - 1; ++j) {
+      if (ld_volatile_shared(&ctl->fail) != 0) break;
+      int i = (j + 1) + ((warp - (j + 1)) & (T - 1));   // this warp's first row below j
+      if (i >= nt) continue;
+      if (i == j + 1) {
+        if (!pivot_row(j)) break;
+        i += T;
+      }
+      if (j < 0 || i >= nt) continue;
+      const Cols q = load_cols(j);
+      bool row_ok = false, diag_ok = false;
+      bool ok = true;
+      for (; ok && i + T < nt; i += 2 * T) {
+        const int ii[2] = {i, i + T};
+        ok = panel<2>(ii, j, q, row_ok, diag_ok);
+      }
+      if (ok && i < nt) {
+        const int ii[1] = {i};
+        ok = panel<1>(ii, j, q, row_ok, diag_ok);
+      }
+      if (!ok) break;
+    }
+  }
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(kOnchipMaxWarps * 32, 1)
+logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta, long long B, long long ld,
+                   const double* __restrict__ hostmean, GatherOut out, int* __restrict__ info, unsigned flags,
+                   unsigned* counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  const OnchipSmem lay(od.nt_max, od.n_groups, pd.P, kernel_has_aux<KIND>());
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+  double* exptab = sm;
+  double* th = sm + lay.off_theta;
+  double* ldg = sm + lay.off_ldg;
+  double* zzg = sm + lay.off_zzg;
+  OnchipCtl* ctl = reinterpret_cast<OnchipCtl*>(sm + lay.off_ctl);
+  double* xs = sm + lay.off_vec;
+  double* bs = xs + lay.vstride;
+  double* rs = bs + lay.vstride;
+  double* e2 = rs + lay.vstride;
+  double* zs = e2 + lay.vstride;
+  double* aux = kernel_has_aux<KIND>() ? zs + lay.vstride : xs;
+
+  for (int i = tid; i < 64; i += nthreads) exptab[i] = kExp2Tab[i];
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) ctl->next = (int)atomicAdd(counter, 1u);
+    __syncthreads();
+    const long long it = ctl->next;
+    if (it >= B) break;
+
+    // ---- theta (gausSN.py:173-194: kernel | mean | lensing, fixed slots from the handle)
+    for (int k = tid; k < pd.P; k += nthreads) {
+      const int col = pd.theta_col[k];
+      th[k] = (col >= 0) ? theta[it * ld + col] : pd.theta_fixed[k];
+    }
+    if (tid == 0) ctl->fail = 0;
+    __syncthreads();
+    const double* mp = th + pd.nk;
+    const double* lp = th + pd.nk + pd.nm;
+    OnchipTeam<KIND> team;
+    team.kc = kernel_consts<KIND>(th);
+    team.exptab = exptab; team.xs = xs; team.bs = bs; team.rs = rs; team.e2 = e2; team.aux = aux; team.zs = zs;
+    team.tiles = reinterpret_cast<double2*>(sm + lay.off_tiles) + lane;
+    team.ctl = ctl; team.ldg = ldg; team.lane = lane; team.T = nthreads >> 5; team.n_total = pd.N;
+    const KernelConsts& kc = team.kc;
+    // a non-finite kernel constant or shifted epoch makes the covariance NaN, which the reference's Cholesky turns into
+    // NaN: detected here, once per theta, so that the N^2 build can use the branch-free exp core
+    int bad = (tid == 0) && !(isfinite(kc.amp) && isfinite(kc.c1) && isfinite(kc.c2) && isfinite(kc.c3) && isfinite(kc.c4));
+    bool dead = false;
+
+    for (int blk = 0; blk < od.n_blocks; ++blk) {
+      const int4 bd = od.blk[blk];
+      const int r0 = bd.x, nt = bd.y, g0 = bd.z, nrows = bd.w;
+      // ---- per-epoch vectors of the block: shifted epochs, magnifications, residual (gausSN.py:139-142)
+      for (int n = tid; n < 8 * nt; n += nthreads) {
+        double x_s = 0.0, b = 0.0, r = 0.0, ax = 0.0, e = 1.0;
+        const int u = od.urow[r0 + n];
+        if (u >= 0) {
+          lens_eval(pd.lens_kind, lp, od.img[r0 + n], od.x[r0 + n], x_s, b);
+          const double m = hostmean ? hostmean[it * pd.N + u] : mean_eval(pd.mean_kind, mp, x_s);
+          r = b * m - od.y[r0 + n];
+          e = od.yerr2[r0 + n];
+          if (kernel_has_aux<KIND>()) ax = kernel_aux<KIND>(kc, x_s);
+          bad |= !isfinite(x_s) || !isfinite(ax);
+        }
+        xs[n] = x_s; bs[n] = b; rs[n] = r; e2[n] = e;
+        if (kernel_has_aux<KIND>()) aux[n] = ax;
+      }
+      if (tid == 0) { ctl->prog_row = 1; ctl->prog_diag = 0; ctl->prog_z = 0; }
+      if (__syncthreads_or(bad)) { dead = true; break; }
+      bad = 0;
+      team.nt = nt; team.nrows = nrows; team.urow = od.urow + r0;
+      team.factor(warp);
+      __syncthreads();
+      if (ctl->fail != 0) break;
+      // z^T z per 32-row group: lane 4 g + q sums the squares of its two columns over the group's tiles
+      if (warp == 0) {
+        const int g = lane >> 2, q = lane & 3;
+        double ss = 0.0;
+        for (int b = 0; b < 4; ++b) {
+          const int t = 4 * g + b;
+          if (t < nt) {
+            const double2 z2 = *reinterpret_cast<const double2*>(zs + 8 * t + 2 * q);
+            ss = fma(z2.x, z2.x, ss);
+            ss = fma(z2.y, z2.y, ss);
+          }
+        }
+        ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        if (q == 0 && 4 * g < nt) {
+          zzg[g0 + g] = ss;
+          ldg[g0 + g] = log(ctl->gmant[g]) + (double)ctl->gexpo[g] * 0.6931471805599453094;
+        }
+      }
+    }
+
+    // ---- logL = -1/2 (N ln 2 pi + ln det + z^T z)      gausSN.py:151-158
+    __syncthreads();
+    if (tid == 0) {
+      double ll;
+      int inf = 0;
+      if (dead) { ll = nan(""); inf = -1; }
+      else if (ctl->fail != 0) { ll = nan(""); inf = ctl->fail; }
+      else {
+        double zsum = 0.0, ldsum = 0.0;
+        for (int g = 0; g < od.n_groups; ++g) { zsum += zzg[g]; ldsum += ldg[g]; }   // fixed order: run-to-run identical
+        ll = -0.5 * (pd.nlog2pi + ldsum + zsum);
+        if (!isfinite(ll)) inf = -1;
+      }
+      if ((flags & GSN_FLAG_NEG_INF) && !isfinite(ll)) ll = -INFINITY;
+      for (int r = 0; r < out.n; ++r) out.ptr[r][out.offset + it] = ll;
+      if (info) info[it] = inf;
+    }
+  }
+}
+
+}  // namespace gsn

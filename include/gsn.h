@@ -98,12 +98,16 @@ typedef enum gsn_query_what {
   GSN_Q_PATH = 10,           /* launch shape of the handle's most recent batch call (gsn_path; 0 before the first) */
   GSN_Q_CLUSTER2_MAX = 11,   /* largest batch that runs one theta per cluster of 2 / 4 / 8 CTAs (0: size not used at this N) */
   GSN_Q_CLUSTER4_MAX = 12,
-  GSN_Q_CLUSTER8_MAX = 13
+  GSN_Q_CLUSTER8_MAX = 13,
+  GSN_Q_ONCHIP = 14,         /* 1 if the handle's batch calls run with the factor resident in shared memory (GSN_PATH_ONCHIP) */
+  GSN_Q_ONCHIP_WARPS = 15,   /* warps that shared one theta in the most recent such launch */
+  GSN_Q_ONCHIP_SMEM = 16     /* bytes of shared memory one theta occupies in that shape */
 } gsn_query_what;
 
 typedef enum gsn_path {
   GSN_PATH_DMMA_BLOCKED = 1,        /* four warps per theta (band blocks above 336 rows, or smaller batches): blocked left-looking Cholesky, FP64 DMMA updates, L in a global workspace */
   GSN_PATH_DMMA_BLOCKED_NARROW = 2, /* the same kernel, one warp per theta (largest band block <= 336 rows and B >= 512, or >= 1024 above 224 rows) */
+  GSN_PATH_ONCHIP = 4,              /* every band block has at most 224 rows: factor resident in shared memory at 8-row granularity, 1-16 warps per theta, no workspace (any batch size) */
   GSN_PATH_DMMA_CLUSTER = 3         /* latency-bound calls (N >= 256, at most as many thetas as clusters fit on the GPU): a thread-block cluster of 2, 4 or 8 four-warp CTAs shares one theta */
 } gsn_path;
 

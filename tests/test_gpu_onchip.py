@@ -1,0 +1,142 @@
+"""The on-chip launch shape (gsn_onchip.cuh): band blocks of at most 224 rows are factored with the Cholesky factor
+resident in shared memory, at 8-row granularity, by teams of 1-16 warps per theta.  Its tile arithmetic is that of the
+workspace kernels (gsn_chol_dmma.cuh) in the same order, so the two must agree bit for bit; both must agree with the
+oracle within |dlogL| <= max(1e-8, 1e-12 |logL|)."""
+import numpy as np
+import pytest
+
+from conftest import assert_logl_close
+from oracle import gp_oracle
+from test_gpu_parity import _synth, _theta_box, _gp_for, _oracle_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _legacy(monkeypatch, ds, kernel, mean, lens, n_images, theta, **kw):
+    """The same problem through the workspace kernels (GSN_FORCE_SHAPE=legacy is read when the handle is created)."""
+    from gaussn_b200 import _engine
+    monkeypatch.setenv("GSN_FORCE_SHAPE", "legacy")
+    gp = _gp_for(ds, kernel, mean, lens, n_images, theta[0])
+    out = gp.loglikelihood_batch(theta, **kw)
+    assert gp._problem.query(_engine.Q_ONCHIP) == 0 and gp._problem.query(_engine.Q_PATH) != _engine.PATH_ONCHIP
+    monkeypatch.delenv("GSN_FORCE_SHAPE")
+    return out
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 7, 8, 9, 15, 16, 17, 31, 32, 33, 40, 63, 64, 65, 96, 100, 141, 160, 161, 192, 194, 217, 224])
+def test_every_order_up_to_224_matches_oracle_and_workspace_kernels(libgsn, monkeypatch, N):
+    from gaussn_b200 import _engine
+    rng = np.random.default_rng(5000 + N)
+    n_images = 2 if N >= 2 else 1
+    ds = _synth(rng, N, 1, n_images)
+    theta = _theta_box(rng, 48, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", n_images)
+    theta[5, 0] = -abs(theta[5, 0]) if N > 1 else theta[5, 0]
+    gp = _gp_for(ds, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", n_images, theta[0])
+    got, info = gp.loglikelihood_batch(theta), None
+    assert gp._problem.query(_engine.Q_ONCHIP) == 1 and gp._problem.query(_engine.Q_PATH) == _engine.PATH_ONCHIP
+    assert_logl_close(got, _oracle_batch(ds, theta, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", gp), f"on-chip N={N}")
+    np.testing.assert_array_equal(got, _legacy(monkeypatch, ds, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", n_images, theta))
+
+
+def test_order_225_uses_the_workspace_kernels(libgsn):
+    from gaussn_b200 import _engine
+    rng = np.random.default_rng(1)
+    ds = _synth(rng, 225, 1, 2)
+    theta = _theta_box(rng, 8, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", 2)
+    gp = _gp_for(ds, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", 2, theta[0])
+    gp.loglikelihood_batch(theta)
+    assert gp._problem.query(_engine.Q_ONCHIP) == 0
+
+
+@pytest.mark.parametrize("kernel", ["ExpSquaredKernel", "ExponentialKernel", "ConstantKernel", "Matern32Kernel", "Matern52Kernel",
+                                    "OUKernel", "GibbsKernel", "PeriodicKernel", "RationalQuadraticKernel", "JJKernel"])
+@pytest.mark.parametrize("n_bands,n_images,N", [(1, 3, 141), (4, 2, 194), (3, 4, 396)])
+def test_every_kernel_on_the_reference_shapes(libgsn, monkeypatch, kernel, n_bands, n_images, N):
+    """The quasar notebook's shape (N = 141, 3 images), the SN notebook's (4 bands x 2 images, N = 194) and BASELINE
+    config 2 (3 bands x 4 images, N = 396)."""
+    from gaussn_b200 import _engine
+    rng = np.random.default_rng(N + 17 * n_bands)
+    ds = _synth(rng, N, n_bands, n_images)
+    theta = _theta_box(rng, 40, kernel, "UniformMean", "ConstantMagnification", n_images)
+    gp = _gp_for(ds, kernel, "UniformMean", "ConstantMagnification", n_images, theta[0])
+    got = gp.loglikelihood_batch(theta)
+    assert gp._problem.query(_engine.Q_PATH) == _engine.PATH_ONCHIP
+    assert_logl_close(got, _oracle_batch(ds, theta, kernel, "UniformMean", "ConstantMagnification", gp), f"{kernel} {n_bands}x{n_images} N={N}")
+    np.testing.assert_array_equal(got, _legacy(monkeypatch, ds, kernel, "UniformMean", "ConstantMagnification", n_images, theta))
+
+
+@pytest.mark.parametrize("n_bands,n_images,N,kernel", [(1, 2, 64, "ExpSquaredKernel"), (1, 3, 141, "OUKernel"), (4, 2, 194, "Matern32Kernel"),
+                                                       (3, 4, 396, "Matern32Kernel"), (2, 2, 448, "Matern52Kernel"), (7, 1, 100, "ExpSquaredKernel")])
+def test_team_size_and_batch_order_do_not_change_a_bit(libgsn, monkeypatch, n_bands, n_images, N, kernel):
+    """1, 2, 4, 8 or 16 warps per theta; 700 thetas (several waves of the persistent grid), 40, 3 and 1 per call; reversed."""
+    from gaussn_b200 import _engine
+    rng = np.random.default_rng(N * 3 + n_bands)
+    ds = _synth(rng, N, n_bands, n_images)
+    lens = "ConstantMagnification" if n_images > 1 else "NoLensing"
+    theta = _theta_box(rng, 700, kernel, "UniformMean", lens, n_images)
+    theta[11, 1] = np.nan                       # a theta that cannot be evaluated, inside the batch
+    gp = _gp_for(ds, kernel, "UniformMean", lens, n_images, theta[0])
+    ref = gp.loglikelihood_batch(theta)
+    assert np.isnan(ref[11]) and np.isfinite(ref).sum() > 600
+    seen = {int(gp._problem.query(_engine.Q_ONCHIP_WARPS))}
+    for T in (1, 2, 4, 8, 16):
+        monkeypatch.setenv("GSN_ONCHIP_T", str(T))
+        np.testing.assert_array_equal(gp.loglikelihood_batch(theta), ref, err_msg=f"T={T}")
+        assert gp._problem.query(_engine.Q_ONCHIP_WARPS) == T
+        np.testing.assert_array_equal(gp.loglikelihood_batch(theta[:3]), ref[:3], err_msg=f"T={T}, 3 thetas")
+    monkeypatch.delenv("GSN_ONCHIP_T")
+    np.testing.assert_array_equal(gp.loglikelihood_batch(theta[::-1].copy())[::-1], ref)
+    np.testing.assert_array_equal(np.concatenate([gp.loglikelihood_batch(theta[i:i + 40]) for i in range(0, 200, 40)]), ref[:200])
+    seen.add(int(gp._problem.query(_engine.Q_ONCHIP_WARPS)))
+    np.testing.assert_array_equal(np.array([gp.loglikelihood_batch(theta[i:i + 1])[0] for i in range(12)]), ref[:12])
+    seen.add(int(gp._problem.query(_engine.Q_ONCHIP_WARPS)))
+    print("team sizes chosen by the dispatch for 700 / 40 / 1 thetas:", sorted(seen))
+    assert_logl_close(ref[:64], _oracle_batch(ds, theta[:64], kernel, "UniformMean", lens, gp), "team")
+
+
+@pytest.mark.parametrize("mean", ["UniformMean", "Sin", "Gaussian", "ExpFunction", "Bazin2009", "Karpenka2012", "Villar2019"])
+@pytest.mark.parametrize("lens", ["NoLensing", "ConstantMagnification", "SigmoidMagnification"])
+def test_every_mean_and_lensing_model_on_chip(libgsn, monkeypatch, mean, lens):
+    from gaussn_b200 import _engine
+    rng = np.random.default_rng(abs(hash(mean + lens)) % 2**31)
+    n_images = 1 if lens == "NoLensing" else 3
+    ds = _synth(rng, 170, 2, n_images)
+    theta = _theta_box(rng, 32, "Matern32Kernel", mean, lens, n_images)
+    gp = _gp_for(ds, "Matern32Kernel", mean, lens, n_images, theta[0])
+    got = gp.loglikelihood_batch(theta)
+    assert gp._problem.query(_engine.Q_PATH) == _engine.PATH_ONCHIP
+    assert_logl_close(got, _oracle_batch(ds, theta, "Matern32Kernel", mean, lens, gp), mean + "/" + lens)
+    np.testing.assert_array_equal(got, _legacy(monkeypatch, ds, "Matern32Kernel", mean, lens, n_images, theta))
+
+
+def test_failure_info_is_the_callers_row(libgsn, monkeypatch):
+    """info = 1-based index, in the caller's row order, of the first non-positive pivot -- the same in both shapes, also
+    with a band mask (where the internal layouts differ)."""
+    from gaussn_b200 import _engine
+    rng = np.random.default_rng(12)
+    ds = _synth(rng, 150, 3, 2)
+    theta = _theta_box(rng, 16, "RationalQuadraticKernel", "UniformMean", "ConstantMagnification", 2)
+    theta[:, 0] *= 40.0        # A^2 (1 + d^2 / ...) with a large amplitude: indefinite early on
+    gp = _gp_for(ds, "RationalQuadraticKernel", "UniformMean", "ConstantMagnification", 2, theta[0])
+    gp.loglikelihood_batch(theta)
+    out, info = gp._problem.logl_host(theta, 0, return_info=True)
+    assert np.isnan(out).any() and np.all((info > 0) == np.isnan(out)) and info.max() <= 150
+    monkeypatch.setenv("GSN_FORCE_SHAPE", "legacy")
+    gp2 = _gp_for(ds, "RationalQuadraticKernel", "UniformMean", "ConstantMagnification", 2, theta[0])
+    gp2.loglikelihood_batch(theta)
+    out2, info2 = gp2._problem.logl_host(theta, 0, return_info=True)
+    np.testing.assert_array_equal(out, out2)
+    np.testing.assert_array_equal(info, info2)
+
+
+def test_new_observations_reach_the_on_chip_tables(libgsn):
+    rng = np.random.default_rng(55)
+    ds = _synth(rng, 90, 2, 2)
+    theta = _theta_box(rng, 20, "Matern32Kernel", "UniformMean", "ConstantMagnification", 2)
+    gp = _gp_for(ds, "Matern32Kernel", "UniformMean", "ConstantMagnification", 2, theta[0])
+    gp.loglikelihood_batch(theta)
+    handle = gp._problem
+    ds2 = dict(ds, y=ds["y"] * 1.1 + 0.01, yerr=ds["yerr"] * 0.9, x=ds["x"] + 0.25)
+    got = gp.loglikelihood_batch(theta, x=ds2["x"], y=ds2["y"], yerr=ds2["yerr"])
+    assert gp._problem is handle
+    assert_logl_close(got, _oracle_batch(ds2, theta, "Matern32Kernel", "UniformMean", "ConstantMagnification", gp), "set_data")
