@@ -74,9 +74,10 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = _nvcc()
     os.makedirs(OBJ_DIR, exist_ok=True)
+    extra = os.environ.get("GSN_EXTRA_NVCC_FLAGS", "").split()   # experiments (e.g. -DGSN_ONCHIP_TRACE=20); never set in shipped builds
     procs = []
     for name, src, defs in UNITS:
-        cmd = [nvcc, *NVCC_FLAGS, *defs, "-c", "-o", os.path.join(OBJ_DIR, name + ".o"), os.path.join(CSRC, src)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *defs, "-c", "-o", os.path.join(OBJ_DIR, name + ".o"), os.path.join(CSRC, src)]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]
             print(" ".join(cmd))

@@ -80,7 +80,7 @@ struct gsn_problem {
   int4* d_oc_blk = nullptr; double* d_oc_x = nullptr; double* d_oc_y = nullptr; double* d_oc_yerr2 = nullptr;
   int* d_oc_img = nullptr; int* d_oc_urow = nullptr;
   std::vector<int> h_oc_urow;
-  size_t smem_onchip = 0; int onchip_ctas_smem = 0, onchip_regs = 0;
+  size_t smem_onchip = 0, smem_onchip_spec = 0; int onchip_ctas_smem = 0, onchip_regs = 0;
   int last_shape = 0;
   int last_warps = 0;     // warps per theta of the most recent on-chip launch
   int n_theta_cols = 0;   // columns the caller's theta must provide
@@ -131,13 +131,18 @@ int dispatch_logl_out(gsn_problem* p, const double* theta, int64_t B, int64_t ld
     while (t_cap < gsn::kOnchipMaxWarps && 2 * t_cap <= p->od.nt_max) t_cap *= 2;   // a team larger than the tile rows idles
     int T = 1;
     while (T < t_cap && T * p->onchip_ctas_smem < target) T *= 2;
+    if (T == 4 && p->od.nt_max < 4) T = 2;   // a specialised team (one pivot warp + three row owners) needs rows to own
     while (T < t_cap && B * T * 2 <= (int64_t)p->sm_count * 4) T *= 2;               // few thetas: shorter critical path per theta
     if (const char* e = getenv("GSN_ONCHIP_T")) T = std::max(1, std::min(gsn::kOnchipMaxWarps, atoi(e)));
-    const int ctas = std::max(1, std::min(std::min(p->onchip_ctas_smem, 32), warps_max / T));
+    const bool spec = T >= 4;    // teams of four and more: a pivot warp on its own SM sub-partition (gsn_onchip.cuh)
+    const size_t smem = spec ? p->smem_onchip_spec : p->smem_onchip;
+    const int ctas_smem = std::max(1, (int)((size_t)(227 * 1024) / (smem + 1024)));
+    int ctas = std::max(1, std::min(std::min(ctas_smem, 32), warps_max / T));
+    if (const char* e = getenv("GSN_ONCHIP_CTAS")) ctas = std::max(1, std::min(ctas, atoi(e)));   // tuning hook
     const int grid = (int)std::min<int64_t>(B, (int64_t)p->sm_count * ctas);
     p->last_shape = GSN_PATH_ONCHIP;
     p->last_warps = T;
-    gsn::OnchipLaunchArgs a{p->pd, p->od, theta, B, ld, hostmean, out, info, flags, p->d_counter, grid, T, p->smem_onchip, stream};
+    gsn::OnchipLaunchArgs a{p->pd, p->od, theta, B, ld, hostmean, out, info, flags, p->d_counter, grid, T, smem, stream};
     const cudaError_t e = (k <= 4) ? gsn::launch_logl_onchip_a(k, &a, nullptr) : gsn::launch_logl_onchip_b(k, &a, nullptr);
     if (e != cudaSuccess) return fail(GSN_ERR_CUDA, "on-chip log-likelihood kernel launch failed: %s", cudaGetErrorString(e));
     p->launches += 1;
@@ -529,7 +534,7 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
     int max_rows = 8 * gsn::kOnchipMaxTiles;
     if (const char* e = getenv("GSN_ONCHIP_MAX_ROWS")) max_rows = atoi(e);   // tuning hook; 0 switches the shape off
     const char* shape_env = getenv("GSN_FORCE_SHAPE");                       // any forced legacy shape switches it off as well
-    const gsn::OnchipSmem lay(nt_max, groups, pd.P, has_aux);
+    const gsn::OnchipSmem lay(nt_max, groups, pd.P, has_aux, true);
     if (!shape_env && nt_max <= gsn::kOnchipMaxTiles && 8 * nt_max <= max_rows + 7 && (int)blk.size() <= gsn::kOnchipMaxBlocks &&
         lay.bytes <= 226 * 1024) {
       const size_t nr = urow.size();
@@ -556,7 +561,8 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
       p->od.blk = p->d_oc_blk; p->od.x = p->d_oc_x; p->od.y = p->d_oc_y; p->od.yerr2 = p->d_oc_yerr2;
       p->od.img = p->d_oc_img; p->od.urow = p->d_oc_urow;
       p->h_oc_urow = urow;
-      p->smem_onchip = lay.bytes;
+      p->smem_onchip_spec = lay.bytes;
+      p->smem_onchip = gsn::OnchipSmem(nt_max, groups, pd.P, has_aux, false).bytes;
       p->onchip_ctas_smem = std::max(1, (int)((size_t)(227 * 1024) / (lay.bytes + 1024)));
       GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_onchip_a(kernel_kind, nullptr, &p->onchip_regs)
                                     : gsn::launch_logl_onchip_b(kernel_kind, nullptr, &p->onchip_regs));

@@ -12,15 +12,19 @@ static cudaError_t prepare_one(int* regs) {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (!attr_set[dev & 63]) {
-    e = cudaFuncSetAttribute(logl_onchip_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    e = cudaFuncSetAttribute(logl_onchip_kernel<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(logl_onchip_kernel<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
   if (regs) {
-    cudaFuncAttributes fa;
-    e = cudaFuncGetAttributes(&fa, logl_onchip_kernel<KIND>);
+    cudaFuncAttributes fa, fb;
+    e = cudaFuncGetAttributes(&fa, logl_onchip_kernel<KIND, false>);
     if (e != cudaSuccess) return e;
-    *regs = fa.numRegs;
+    e = cudaFuncGetAttributes(&fb, logl_onchip_kernel<KIND, true>);
+    if (e != cudaSuccess) return e;
+    *regs = fa.numRegs > fb.numRegs ? fa.numRegs : fb.numRegs;
   }
   return cudaSuccess;
 }
@@ -29,8 +33,12 @@ template <int KIND>
 static cudaError_t launch_one(const OnchipLaunchArgs& a) {
   cudaError_t e = prepare_one<KIND>(nullptr);
   if (e != cudaSuccess) return e;
-  logl_onchip_kernel<KIND><<<a.grid, a.warps * 32, a.smem_bytes, a.stream>>>(a.pd, a.od, a.theta, a.B, a.ld, a.hostmean, a.out, a.info,
-                                                                             a.flags, a.counter);
+  if (a.warps >= 4)
+    logl_onchip_kernel<KIND, true><<<a.grid, a.warps * 32, a.smem_bytes, a.stream>>>(a.pd, a.od, a.theta, a.B, a.ld, a.hostmean, a.out,
+                                                                                     a.info, a.flags, a.counter);
+  else
+    logl_onchip_kernel<KIND, false><<<a.grid, a.warps * 32, a.smem_bytes, a.stream>>>(a.pd, a.od, a.theta, a.B, a.ld, a.hostmean, a.out,
+                                                                                      a.info, a.flags, a.counter);
   return cudaGetLastError();
 }
 
@@ -43,6 +51,12 @@ static cudaError_t dispatch(int kind, const OnchipLaunchArgs* a, int* regs) {   
     return dispatch<KIND + 1>(kind, a, regs);
   }
 }
+
+#if defined(GSN_ONCHIP_TRACE) && GSN_SLICE_LO == 0
+extern "C" int gsn_debug_onchip_trace(long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, g_onchip_trace, sizeof(long long) * (size_t)n);
+}
+#endif
 
 cudaError_t GSN_SLICE_NAME(int kind, const OnchipLaunchArgs* a, int* regs) { return dispatch<GSN_SLICE_LO>(kind, a, regs); }
 

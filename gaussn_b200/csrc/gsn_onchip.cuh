@@ -36,6 +36,9 @@
 
 namespace gsn {
 
+#ifndef GSN_ONCHIP_DIAG_TILE
+#define GSN_ONCHIP_DIAG_TILE false   // pivots by shuffle from the tile's own diagonal (see chol8_inv_warp)
+#endif
 constexpr int kOnchipMaxTiles = 28;    // largest band block: 224 rows (406 tiles = 203 KB)
 constexpr int kOnchipMaxWarps = 16;
 constexpr int kOnchipMaxBlocks = 256;
@@ -58,15 +61,17 @@ struct OnchipCtl {
   int prog_row;        // rows [0, prog_row) are stored through their last off-diagonal tile
   int prog_diag;       // pivot tiles [0, prog_diag) are factored: -inv(L(j,j)) is stored
   int prog_z;          // z(0) ... z(prog_z - 1) are stored
+  int pre_ready;       // specialised teams: rows [1, pre_ready] are stored through column row - 2 and their accumulators handed over
   double gmant[8];     // pivot product of each 32-row group of the block in work, as mantissa ...
   int gexpo[8];        // ... and exponent; the logarithms are taken after the factorisation, off its critical path
 };
 
 // Shared-memory carve-up (offsets in doubles).
+constexpr int kPreSlot = 80;   // double2 units per hand-over slot: S [0, 32), D [32, 64), y (one double per lane) [64, 80)
 struct OnchipSmem {
-  int off_theta, off_ldg, off_zzg, off_ctl, off_vec, off_tiles, vstride;
+  int off_theta, off_ldg, off_zzg, off_ctl, off_vec, off_pre, off_tiles, vstride;
   size_t bytes;
-  __host__ __device__ OnchipSmem(int nt_max, int n_groups, int P, bool has_aux) {
+  __host__ __device__ OnchipSmem(int nt_max, int n_groups, int P, bool has_aux, bool spec) {
     int o = 64;                                   // 2^(j/64) table of fast_exp
     off_theta = o; o += (P + 1) & ~1;
     off_ldg = o; o += n_groups;
@@ -75,6 +80,7 @@ struct OnchipSmem {
     off_ctl = o; o += (int)((sizeof(OnchipCtl) + 15) / 16 * 2);   // vectors and tiles are accessed 16 bytes at a time
     vstride = 8 * nt_max;
     off_vec = o; o += vstride * (has_aux ? 6 : 5);   // shifted epochs, magnifications, residual, yerr^2, z, [aux]
+    off_pre = o; if (spec) o += 4 * kPreSlot * 2;      // hand-over ring between the row owners and the pivot warp
     off_tiles = o; o += nt_max * (nt_max + 1) / 2 * 64;
     bytes = (size_t)o * 8;
   }
@@ -88,8 +94,18 @@ __device__ __forceinline__ bool onchip_wait_gt(const int* p, int v, const int* f
   return true;
 }
 
+#ifdef GSN_ONCHIP_TRACE
+// Debug build only: per-column timestamps of one theta (CTA 0, its GSN_ONCHIP_TRACE-th theta), read back by tools/.
+__device__ long long g_onchip_trace[8192];
+#define GSN_TRACE(slot, col) do { if (trace_on && lane == 0) g_onchip_trace[((col) + 1) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define GSN_TRACE(slot, col) do { } while (0)
+#endif
+
 template <int KIND>
 struct OnchipTeam {
+  bool trace_on = false;
+  double2* pre;        // hand-over ring (specialised teams)
   KernelConsts kc;
   const double* exptab;
   const double *xs, *bs, *rs, *e2, *aux;
@@ -132,8 +148,24 @@ struct OnchipTeam {
   }
 
   __device__ __forceinline__ static int tri(int i) { return i * (i + 1) / 2; }
-  __device__ __forceinline__ double2 zfrag(int k) const {   // z(k) as row 0 of an operand tile
-    return (lane < 4) ? *reinterpret_cast<const double2*>(zs + 8 * k + 2 * lane) : make_double2(0.0, 0.0);
+  // Residual row.  y(i) = sum_k L(i,k) z(k) is accumulated as one partial sum per lane (its two columns of every tile, two
+  // DFMAs per tile: an 8x8 matrix-vector product issued as DMMAs would occupy the FP64 pipe eight times as long), reduced over
+  // the four lanes of a row at the end; z(i) = inv(L(i,i)) (r(i) - y(i)).
+  __device__ __forceinline__ double2 zpair(int k) const { return *reinterpret_cast<const double2*>(zs + 8 * k + 2 * (lane & 3)); }
+  __device__ __forceinline__ static double ydot(double y, const double2& a, const double2& z) { return fma(a.y, z.y, fma(a.x, z.x, y)); }
+  // returns z(i) of this lane's row; stores it
+  __device__ __forceinline__ double finish_z(int i, double y, const double2& nW) const {
+    constexpr unsigned kFull = 0xffffffffu;
+    const int r = lane >> 2, q = lane & 3;
+    y += __shfl_xor_sync(kFull, y, 1);
+    y += __shfl_xor_sync(kFull, y, 2);
+    const double t = y - rs[8 * i + r];                       // -(r - L z), row r
+    const double t0 = __shfl_sync(kFull, t, 8 * q), t1 = __shfl_sync(kFull, t, 8 * q + 4);   // rows 2q, 2q + 1
+    double p = fma(nW.y, t1, nW.x * t0);                      // nW = -inv(L(i,i))
+    p += __shfl_xor_sync(kFull, p, 1);
+    p += __shfl_xor_sync(kFull, p, 2);
+    if (q == 0) zs[8 * i + r] = p;
+    return p;
   }
 
   // Column j for R of this warp's rows: T(i[r], j).  Returns false if the theta failed while waiting.
@@ -181,32 +213,32 @@ struct OnchipTeam {
   // Everything else (the GEMMs over k < j, the residual row Z, the pivot products) is kept off it.
   __device__ __forceinline__ bool pivot_row(int j) const {
     const int i = j + 1;
+    GSN_TRACE(0, j);
     const Cols qi = load_cols(i);
     double2 S = make_double2(0.0, 0.0), X = make_double2(0.0, 0.0);
     double2 D = build(i, i, qi);
-    double2 Z = make_double2(0.0, 0.0);
-    if (lane < 4) {
-      const double2 r2 = *reinterpret_cast<const double2*>(rs + 8 * i + 2 * lane);
-      Z = make_double2(-r2.x, -r2.y);
-    }
+    double y = 0.0;
     double2* Ap = tiles + tri(i) * 32;
     if (j >= 0) {
       S = build(i, j, load_cols(j));
+      GSN_TRACE(1, j);
       if (T > 1 && !(onchip_wait_gt(&ctl->prog_row, j, &ctl->fail) && onchip_wait_gt(&ctl->prog_z, j - 1, &ctl->fail))) return false;
+      GSN_TRACE(2, j);
       const double2* Bp = tiles + tri(j) * 32;
 #pragma unroll 2
       for (int k = 0; k < j; ++k) {
         const double2 b = Bp[k * 32];
         const double2 a = Ap[k * 32];
-        const double2 z = zfrag(k);
+        const double2 z = zpair(k);
         dmma(S, a.x, b.x);
         dmma(D, a.x, a.x);
-        dmma(Z, z.x, a.x);
         dmma(S, a.y, b.y);
         dmma(D, a.y, a.y);
-        dmma(Z, z.y, a.y);
+        y = ydot(y, a, z);
       }
+      GSN_TRACE(3, j);
       if (T > 1 && !onchip_wait_gt(&ctl->prog_diag, j, &ctl->fail)) return false;
+      GSN_TRACE(4, j);
       const double2 nWj = Bp[j * 32];
       dmma(X, S.x, nWj.x);
       dmma(X, S.y, nWj.y);
@@ -221,23 +253,20 @@ struct OnchipTeam {
     double mant = 1.0;
     int expo = 0, failrow = -1;
     double2 nW;
-    chol8_inv_warp(make_double2(-D.x, -D.y), lane, nW, mant, expo, failrow);
+    GSN_TRACE(5, j);
+    chol8_inv_warp<GSN_ONCHIP_DIAG_TILE>(make_double2(-D.x, -D.y), lane, nW, mant, expo, failrow);
     Ap[i * 32] = nW;
     if (T > 1) {
       __syncwarp();
       if (lane == 0) st_release_shared(&ctl->prog_diag, i + 1);
     }
+    GSN_TRACE(6, j);
     // ---- off the critical path: the residual row, the pivot product, the failure index
     if (j >= 0) {
       if (T > 1 && !onchip_wait_gt(&ctl->prog_z, j, &ctl->fail)) return false;
-      const double2 z = zfrag(j);
-      dmma(Z, z.x, X.x);
-      dmma(Z, z.y, X.y);
+      y = ydot(y, X, zpair(j));
     }
-    double2 Zf = make_double2(0.0, 0.0);
-    dmma(Zf, Z.x, nW.x);
-    dmma(Zf, Z.y, nW.y);
-    if (lane < 4) *reinterpret_cast<double2*>(zs + 8 * i + 2 * lane) = Zf;
+    finish_z(i, y, nW);
     if (lane == 0) {
       if (failrow >= 0) {   // a padding row can only get here through NaNs that an earlier row produced
         const int u = urow[8 * i + failrow];
@@ -250,7 +279,161 @@ struct OnchipTeam {
     }
     __syncwarp();
     if (T > 1 && lane == 0) st_release_shared(&ctl->prog_z, i + 1);
+    GSN_TRACE(7, j);
     return true;
+  }
+
+  // ---------------------------------------------------------------------------------------------------------------------
+  // Specialised team (T >= 4).  An FP64 instruction of a warp that walks a dependent chain waits behind whatever DMMAs the
+  // other warps of its SM sub-partition have queued: the 8x8 elimination takes 1.5 k cycles alone, 18 k next to ONE warp
+  // that streams DMMAs and is starved next to two (bench/chol8_lat.cu; warps on other sub-partitions do not matter) -- and
+  // the pivot chain is the critical path of the factorisation.  So warp 0 does nothing but the chain, the warps of the
+  // other three sub-partitions (warp & 3 != 0) own the rows, and warps 4, 8, 12 of larger teams idle at the barrier:
+  // sub-partition 0 carries no streaming work at all.
+  //   row owner, column j = i - 2 (pre_D): T(i, j), and in the same sweep over k < j the accumulators of the NEXT two
+  //     tiles of row i -- S1 = sum_{k<=i-3} L(i,k) L(i-1,k)^T - K(i,i-1), D(i), Z(i) -- parked in a hand-over slot;
+  //   pivot warp, step i: S1 += L(i,i-2) L(i-1,i-2)^T (the one term that was not available two columns earlier; its second
+  //     operand is the X of the previous step, still in registers), solve, D += X X^T, 8x8 elimination, residual.
+  // Nothing on the chain waits for a GEMM any more.  Same tile arithmetic in the same order: bit-identical to T <= 2.
+  __device__ __forceinline__ double2* pre_slot(int i) const { return pre + (i & 3) * kPreSlot; }
+
+  __device__ __forceinline__ void pivot_chain() const {
+    // -inv(L(i-1,i-1)), z(i-1) and L(i-1,i-2) stay in registers from one step to the next
+    double2 nWprev = make_double2(0.0, 0.0), zprev = make_double2(0.0, 0.0), Xprev = make_double2(0.0, 0.0);
+    constexpr unsigned kFull = 0xffffffffu;
+    for (int i = 0; i < nt; ++i) {
+      double2* Ap = tiles + tri(i) * 32;
+      double2 D, X = make_double2(0.0, 0.0);
+      double y = 0.0;
+      GSN_TRACE(0, i - 1);
+      if (i == 0) {
+        D = build(0, 0, load_cols(0));
+      } else {
+        if (!onchip_wait_gt(&ctl->pre_ready, i - 1, &ctl->fail)) return;
+        GSN_TRACE(4, i - 1);
+        const double2* ps = pre_slot(i);
+        double2 S = ps[lane];
+        D = ps[32 + lane];
+        y = reinterpret_cast<const double*>(ps + 64)[lane];
+        if (i >= 2) {
+          const double2 a = Ap[(i - 2) * 32];
+          dmma(S, a.x, Xprev.x);
+          dmma(S, a.y, Xprev.y);
+        }
+        dmma(X, S.x, nWprev.x);
+        dmma(X, S.y, nWprev.y);
+        Ap[(i - 1) * 32] = X;
+        __syncwarp();
+        if (lane == 0) st_release_shared(&ctl->prog_row, i + 1);
+        dmma(D, X.x, X.x);
+        dmma(D, X.y, X.y);
+      }
+      double mant = 1.0;
+      int expo = 0, failrow = -1;
+      double2 nW;
+      GSN_TRACE(5, i - 1);
+      chol8_inv_warp<GSN_ONCHIP_DIAG_TILE>(make_double2(-D.x, -D.y), lane, nW, mant, expo, failrow);
+      Ap[i * 32] = nW;
+      __syncwarp();
+      if (lane == 0) st_release_shared(&ctl->prog_diag, i + 1);
+      GSN_TRACE(6, i - 1);
+      if (i > 0) y = ydot(y, X, zprev);
+      const double zi = finish_z(i, y, nW);
+      if (lane == 0) {
+        if (failrow >= 0) {
+          const int u = urow[8 * i + failrow];
+          atomicCAS(&ctl->fail, 0, u >= 0 ? u + 1 : n_total);
+        }
+        if ((i & 3) != 0) { mant *= ctl->gmant[i >> 2]; expo += ctl->gexpo[i >> 2]; }
+        ctl->gmant[i >> 2] = mant;
+        ctl->gexpo[i >> 2] = expo;
+      }
+      __syncwarp();
+      if (lane == 0) st_release_shared(&ctl->prog_z, i + 1);
+      GSN_TRACE(7, i - 1);
+      nWprev = nW;
+      Xprev = X;
+      zprev = make_double2(__shfl_sync(kFull, zi, 8 * (lane & 3)), __shfl_sync(kFull, zi, 8 * (lane & 3) + 4));   // z(i)[2q], [2q+1]
+      if (failrow >= 0) return;
+    }
+  }
+
+  // Row 1 has no column two to its left: its accumulators are just the covariance tiles.
+  __device__ __forceinline__ void pre_first() const {
+    double2* ps = pre_slot(1);
+    ps[lane] = build(1, 0, load_cols(0));
+    ps[32 + lane] = build(1, 1, load_cols(1));
+    reinterpret_cast<double*>(ps + 64)[lane] = 0.0;
+    __syncwarp();
+    if (lane == 0) st_release_shared(&ctl->pre_ready, 1);
+  }
+
+  // Column j = i - 2 of row i: T(i, j), and the accumulators of (i, i-1), (i, i) and the residual through column j.
+  __device__ __forceinline__ bool pre_D(int i, int j, const Cols& q) const {
+    double2 S = build(i, j, q);
+    double2 S1 = build(i, i - 1, load_cols(i - 1));
+    double2 D = build(i, i, load_cols(i));
+    double y = 0.0;
+    // row j complete; row i - 1 stored through column j - 1 (its owner's pre_D); z through j - 1
+    if (!(onchip_wait_gt(&ctl->prog_row, j, &ctl->fail) && onchip_wait_gt(&ctl->pre_ready, i - 2, &ctl->fail) &&
+          onchip_wait_gt(&ctl->prog_z, j - 1, &ctl->fail))) return false;
+    const double2* Bp = tiles + tri(j) * 32;
+    const double2* B1p = tiles + tri(i - 1) * 32;
+    double2* Ap = tiles + tri(i) * 32;
+#pragma unroll 2
+    for (int k = 0; k < j; ++k) {
+      const double2 b = Bp[k * 32];
+      const double2 b1 = B1p[k * 32];
+      const double2 a = Ap[k * 32];
+      const double2 z = zpair(k);
+      dmma(S, a.x, b.x);
+      dmma(S1, a.x, b1.x);
+      dmma(D, a.x, a.x);
+      dmma(S, a.y, b.y);
+      dmma(S1, a.y, b1.y);
+      dmma(D, a.y, a.y);
+      y = ydot(y, a, z);
+    }
+    if (!onchip_wait_gt(&ctl->prog_diag, j, &ctl->fail)) return false;
+    const double2 nWj = Bp[j * 32];
+    double2 X = make_double2(0.0, 0.0);
+    dmma(X, S.x, nWj.x);
+    dmma(X, S.y, nWj.y);
+    Ap[j * 32] = X;
+    if (!onchip_wait_gt(&ctl->prog_z, j, &ctl->fail)) return false;
+    dmma(D, X.x, X.x);
+    dmma(D, X.y, X.y);
+    y = ydot(y, X, zpair(j));
+    double2* ps = pre_slot(i);
+    ps[lane] = S1;
+    ps[32 + lane] = D;
+    reinterpret_cast<double*>(ps + 64)[lane] = y;
+    __syncwarp();
+    if (lane == 0) st_release_shared(&ctl->pre_ready, i);
+    return true;
+  }
+
+  // Row owner b of NB: rows 1 + b, 1 + b + NB, ...
+  __device__ __forceinline__ void bulk(int b, int NB) const {
+    if (b == 0 && nt > 1) pre_first();
+    for (int j = 0; j < nt - 1; ++j) {
+      if (ld_volatile_shared(&ctl->fail) != 0) break;
+      int i = j + 1 + (b - j % NB + NB) % NB;   // this warp's first row below j
+      if (i == j + 1) i += NB;                  // tile (j + 1, j) belongs to the pivot warp
+      if (i >= nt) continue;
+      const Cols q = load_cols(j);
+      bool row_ok = false, diag_ok = false, ok = true;
+      if (i == j + 2) { ok = pre_D(i, j, q); row_ok = diag_ok = true; i += NB; }
+      for (; ok && i + NB < nt; i += 2 * NB) {
+        const int ii[2] = {i, i + NB};
+        ok = panel<2>(ii, j, q, row_ok, diag_ok);
+      }
+      if (ok && i < nt) {
+        const int ii[1] = {i};
+        ok = panel<1>(ii, j, q, row_ok, diag_ok);
+      }
+      if (!ok) break;
+    }
   }
 
   __device__ __forceinline__ void factor(int warp) const {
@@ -279,14 +462,14 @@ struct OnchipTeam {
   }
 };
 
-template <int KIND>
+template <int KIND, bool kSpec>
 __global__ void __launch_bounds__(kOnchipMaxWarps * 32, 1)
 logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta, long long B, long long ld,
                    const double* __restrict__ hostmean, GatherOut out, int* __restrict__ info, unsigned flags,
                    unsigned* counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
-  const OnchipSmem lay(od.nt_max, od.n_groups, pd.P, kernel_has_aux<KIND>());
+  const OnchipSmem lay(od.nt_max, od.n_groups, pd.P, kernel_has_aux<KIND>(), kSpec);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
   double* exptab = sm;
   double* th = sm + lay.off_theta;
@@ -301,8 +484,14 @@ logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta
   double* aux = kernel_has_aux<KIND>() ? zs + lay.vstride : xs;
 
   for (int i = tid; i < 64; i += nthreads) exptab[i] = kExp2Tab[i];
+#ifdef GSN_ONCHIP_TRACE
+  int n_done = -1;
+#endif
 
   for (;;) {
+#ifdef GSN_ONCHIP_TRACE
+    ++n_done;
+#endif
     __syncthreads();
     if (tid == 0) ctl->next = (int)atomicAdd(counter, 1u);
     __syncthreads();
@@ -322,6 +511,7 @@ logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta
     team.kc = kernel_consts<KIND>(th);
     team.exptab = exptab; team.xs = xs; team.bs = bs; team.rs = rs; team.e2 = e2; team.aux = aux; team.zs = zs;
     team.tiles = reinterpret_cast<double2*>(sm + lay.off_tiles) + lane;
+    team.pre = reinterpret_cast<double2*>(sm + lay.off_pre);
     team.ctl = ctl; team.ldg = ldg; team.lane = lane; team.T = nthreads >> 5; team.n_total = pd.N;
     const KernelConsts& kc = team.kc;
     // a non-finite kernel constant or shifted epoch makes the covariance NaN, which the reference's Cholesky turns into
@@ -347,12 +537,24 @@ logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta
         xs[n] = x_s; bs[n] = b; rs[n] = r; e2[n] = e;
         if (kernel_has_aux<KIND>()) aux[n] = ax;
       }
-      if (tid == 0) { ctl->prog_row = 1; ctl->prog_diag = 0; ctl->prog_z = 0; }
+      if (tid == 0) { ctl->prog_row = 1; ctl->prog_diag = 0; ctl->prog_z = 0; ctl->pre_ready = 0; }
       if (__syncthreads_or(bad)) { dead = true; break; }
       bad = 0;
       team.nt = nt; team.nrows = nrows; team.urow = od.urow + r0;
-      team.factor(warp);
+#ifdef GSN_ONCHIP_TRACE
+      team.trace_on = (blockIdx.x == 0 && blk == 0 && n_done == GSN_ONCHIP_TRACE);
+      if (team.trace_on && tid == 0) { g_onchip_trace[0] = clock64(); g_onchip_trace[1] = nt; }
+#endif
+      if constexpr (kSpec) {
+        if (warp == 0) team.pivot_chain();
+        else if ((warp & 3) != 0) team.bulk(warp - 1 - (warp >> 2), team.T - (team.T >> 2));
+      } else {
+        team.factor(warp);
+      }
       __syncthreads();
+#ifdef GSN_ONCHIP_TRACE
+      if (team.trace_on && tid == 0) g_onchip_trace[2] = clock64();
+#endif
       if (ctl->fail != 0) break;
       // z^T z per 32-row group: lane 4 g + q sums the squares of its two columns over the group's tiles
       if (warp == 0) {

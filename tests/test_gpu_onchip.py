@@ -1,7 +1,8 @@
 """The on-chip launch shape (gsn_onchip.cuh): band blocks of at most 224 rows are factored with the Cholesky factor
-resident in shared memory, at 8-row granularity, by teams of 1-16 warps per theta.  Its tile arithmetic is that of the
-workspace kernels (gsn_chol_dmma.cuh) in the same order, so the two must agree bit for bit; both must agree with the
-oracle within |dlogL| <= max(1e-8, 1e-12 |logL|)."""
+resident in shared memory, at 8-row granularity, by teams of 1-16 warps per theta.  Results must not depend on the team
+size or the batch (bit for bit), must agree with the oracle within |dlogL| <= max(1e-8, 1e-12 |logL|), and with the
+workspace kernels (gsn_chol_dmma.cuh: same factorisation, residual row and pivot products accumulated in another order)
+ten times closer than that."""
 import numpy as np
 import pytest
 
@@ -10,6 +11,10 @@ from oracle import gp_oracle
 from test_gpu_parity import _synth, _theta_box, _gp_for, _oracle_batch
 
 pytestmark = pytest.mark.gpu
+
+
+def _agree(got, legacy, what=""):
+    assert_logl_close(got, legacy, what + " (on-chip vs workspace kernels)", atol=1e-9, rtol=1e-13)
 
 
 def _legacy(monkeypatch, ds, kernel, mean, lens, n_images, theta, **kw):
@@ -35,7 +40,7 @@ def test_every_order_up_to_224_matches_oracle_and_workspace_kernels(libgsn, monk
     got, info = gp.loglikelihood_batch(theta), None
     assert gp._problem.query(_engine.Q_ONCHIP) == 1 and gp._problem.query(_engine.Q_PATH) == _engine.PATH_ONCHIP
     assert_logl_close(got, _oracle_batch(ds, theta, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", gp), f"on-chip N={N}")
-    np.testing.assert_array_equal(got, _legacy(monkeypatch, ds, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", n_images, theta))
+    _agree(got, _legacy(monkeypatch, ds, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", n_images, theta))
 
 
 def test_order_225_uses_the_workspace_kernels(libgsn):
@@ -62,7 +67,7 @@ def test_every_kernel_on_the_reference_shapes(libgsn, monkeypatch, kernel, n_ban
     got = gp.loglikelihood_batch(theta)
     assert gp._problem.query(_engine.Q_PATH) == _engine.PATH_ONCHIP
     assert_logl_close(got, _oracle_batch(ds, theta, kernel, "UniformMean", "ConstantMagnification", gp), f"{kernel} {n_bands}x{n_images} N={N}")
-    np.testing.assert_array_equal(got, _legacy(monkeypatch, ds, kernel, "UniformMean", "ConstantMagnification", n_images, theta))
+    _agree(got, _legacy(monkeypatch, ds, kernel, "UniformMean", "ConstantMagnification", n_images, theta))
 
 
 @pytest.mark.parametrize("n_bands,n_images,N,kernel", [(1, 2, 64, "ExpSquaredKernel"), (1, 3, 141, "OUKernel"), (4, 2, 194, "Matern32Kernel"),
@@ -106,7 +111,7 @@ def test_every_mean_and_lensing_model_on_chip(libgsn, monkeypatch, mean, lens):
     got = gp.loglikelihood_batch(theta)
     assert gp._problem.query(_engine.Q_PATH) == _engine.PATH_ONCHIP
     assert_logl_close(got, _oracle_batch(ds, theta, "Matern32Kernel", mean, lens, gp), mean + "/" + lens)
-    np.testing.assert_array_equal(got, _legacy(monkeypatch, ds, "Matern32Kernel", mean, lens, n_images, theta))
+    _agree(got, _legacy(monkeypatch, ds, "Matern32Kernel", mean, lens, n_images, theta))
 
 
 def test_failure_info_is_the_callers_row(libgsn, monkeypatch):
@@ -125,7 +130,7 @@ def test_failure_info_is_the_callers_row(libgsn, monkeypatch):
     gp2 = _gp_for(ds, "RationalQuadraticKernel", "UniformMean", "ConstantMagnification", 2, theta[0])
     gp2.loglikelihood_batch(theta)
     out2, info2 = gp2._problem.logl_host(theta, 0, return_info=True)
-    np.testing.assert_array_equal(out, out2)
+    _agree(out, out2)
     np.testing.assert_array_equal(info, info2)
 
 
