@@ -78,9 +78,9 @@ struct gsn_problem {
   bool onchip_ok = false;
   gsn::OnchipDev od{};
   int4* d_oc_blk = nullptr; double* d_oc_x = nullptr; double* d_oc_y = nullptr; double* d_oc_yerr2 = nullptr;
-  int* d_oc_img = nullptr; int* d_oc_urow = nullptr;
+  int* d_oc_img = nullptr; int* d_oc_urow = nullptr; int* d_oc_taboff = nullptr; unsigned char* d_oc_tabs = nullptr;
   std::vector<int> h_oc_urow;
-  size_t smem_onchip = 0, smem_onchip_spec = 0; int onchip_ctas_smem = 0, onchip_regs = 0;
+  size_t smem_onchip = 0; int onchip_ctas_smem = 0, onchip_regs = 0;
   int last_shape = 0;
   int last_warps = 0;     // warps per theta of the most recent on-chip launch
   int n_theta_cols = 0;   // columns the caller's theta must provide
@@ -125,18 +125,17 @@ int dispatch_logl_out(gsn_problem* p, const double* theta, int64_t B, int64_t ld
     // with warps given how many thetas its shared memory holds, and larger for calls with too few thetas to fill the GPU.
     // Results do not depend on T (same tile arithmetic, whoever runs it).
     const int warps_max = std::max(1, std::min(64, 65536 / (((p->onchip_regs + 7) / 8 * 8) * 32)));
-    int target = 16;
+    // (more thetas in flight beat larger teams: N = 160 runs 7.6 M evals/s as 3 x 4 warps per SM against 7.1 M as 2 x 8)
+    int target = 12;
     if (const char* e = getenv("GSN_ONCHIP_WARPS_PER_SM")) target = std::max(1, atoi(e));
     int t_cap = 1;
     while (t_cap < gsn::kOnchipMaxWarps && 2 * t_cap <= p->od.nt_max) t_cap *= 2;   // a team larger than the tile rows idles
     int T = 1;
     while (T < t_cap && T * p->onchip_ctas_smem < target) T *= 2;
-    if (T == 4 && p->od.nt_max < 4) T = 2;   // a specialised team (one pivot warp + three row owners) needs rows to own
     while (T < t_cap && B * T * 2 <= (int64_t)p->sm_count * 4) T *= 2;               // few thetas: shorter critical path per theta
     if (const char* e = getenv("GSN_ONCHIP_T")) T = std::max(1, std::min(gsn::kOnchipMaxWarps, atoi(e)));
-    const bool spec = T >= 4;    // teams of four and more: a pivot warp on its own SM sub-partition (gsn_onchip.cuh)
-    const size_t smem = spec ? p->smem_onchip_spec : p->smem_onchip;
-    const int ctas_smem = std::max(1, (int)((size_t)(227 * 1024) / (smem + 1024)));
+    const size_t smem = p->smem_onchip;
+    const int ctas_smem = p->onchip_ctas_smem;
     int ctas = std::max(1, std::min(std::min(ctas_smem, 32), warps_max / T));
     if (const char* e = getenv("GSN_ONCHIP_CTAS")) ctas = std::max(1, std::min(ctas, atoi(e)));   // tuning hook
     const int grid = (int)std::min<int64_t>(B, (int64_t)p->sm_count * ctas);
@@ -531,10 +530,24 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
       groups += (nt + 3) / 4;
       b0 = b1;
     }
-    int max_rows = 8 * gsn::kOnchipMaxTiles;
+    int max_rows = gsn::kOnchipDispatchRows;
     if (const char* e = getenv("GSN_ONCHIP_MAX_ROWS")) max_rows = atoi(e);   // tuning hook; 0 switches the shape off
     const char* shape_env = getenv("GSN_FORCE_SHAPE");                       // any forced legacy shape switches it off as well
-    const gsn::OnchipSmem lay(nt_max, groups, pd.P, has_aux, true);
+    // live-set slot tables, one per distinct block size
+    std::vector<unsigned char> tabs;
+    std::vector<int> tab_off(blk.size(), 0), off_of_nt(gsn::kOnchipMaxTiles + 1, -1);
+    int n_slots = 0;
+    if (nt_max <= gsn::kOnchipMaxTiles)
+      for (size_t b = 0; b < blk.size(); ++b) {
+        const int nt = blk[b].y;
+        if (off_of_nt[nt] < 0) {
+          off_of_nt[nt] = (int)tabs.size();
+          tabs.resize(tabs.size() + (size_t)nt * (nt + 1) / 2);
+          n_slots = std::max(n_slots, gsn::onchip_slot_table(nt, tabs.data() + off_of_nt[nt]));
+        }
+        tab_off[b] = off_of_nt[nt];
+      }
+    const gsn::OnchipSmem lay(nt_max, n_slots, groups, pd.P, has_aux);
     if (!shape_env && nt_max <= gsn::kOnchipMaxTiles && 8 * nt_max <= max_rows + 7 && (int)blk.size() <= gsn::kOnchipMaxBlocks &&
         lay.bytes <= 226 * 1024) {
       const size_t nr = urow.size();
@@ -551,18 +564,22 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
       GSN_CUDA_P(cudaMalloc(&p->d_oc_yerr2, sizeof(double) * nr));
       GSN_CUDA_P(cudaMalloc(&p->d_oc_img, sizeof(int) * nr));
       GSN_CUDA_P(cudaMalloc(&p->d_oc_urow, sizeof(int) * nr));
+      GSN_CUDA_P(cudaMalloc(&p->d_oc_taboff, sizeof(int) * tab_off.size()));
+      GSN_CUDA_P(cudaMalloc(&p->d_oc_tabs, tabs.size()));
+      GSN_CUDA_P(cudaMemcpy(p->d_oc_taboff, tab_off.data(), sizeof(int) * tab_off.size(), cudaMemcpyHostToDevice));
+      GSN_CUDA_P(cudaMemcpy(p->d_oc_tabs, tabs.data(), tabs.size(), cudaMemcpyHostToDevice));
       GSN_CUDA_P(cudaMemcpy(p->d_oc_blk, blk.data(), sizeof(int4) * blk.size(), cudaMemcpyHostToDevice));
       GSN_CUDA_P(cudaMemcpy(p->d_oc_x, ox.data(), sizeof(double) * nr, cudaMemcpyHostToDevice));
       GSN_CUDA_P(cudaMemcpy(p->d_oc_y, oy.data(), sizeof(double) * nr, cudaMemcpyHostToDevice));
       GSN_CUDA_P(cudaMemcpy(p->d_oc_yerr2, oe.data(), sizeof(double) * nr, cudaMemcpyHostToDevice));
       GSN_CUDA_P(cudaMemcpy(p->d_oc_img, oimg.data(), sizeof(int) * nr, cudaMemcpyHostToDevice));
       GSN_CUDA_P(cudaMemcpy(p->d_oc_urow, urow.data(), sizeof(int) * nr, cudaMemcpyHostToDevice));
-      p->od.n_blocks = (int)blk.size(); p->od.nt_max = nt_max; p->od.n_groups = groups;
+      p->od.n_blocks = (int)blk.size(); p->od.nt_max = nt_max; p->od.n_groups = groups; p->od.n_slots = n_slots;
+      p->od.tab_off = p->d_oc_taboff; p->od.tabs = p->d_oc_tabs;
       p->od.blk = p->d_oc_blk; p->od.x = p->d_oc_x; p->od.y = p->d_oc_y; p->od.yerr2 = p->d_oc_yerr2;
       p->od.img = p->d_oc_img; p->od.urow = p->d_oc_urow;
       p->h_oc_urow = urow;
-      p->smem_onchip_spec = lay.bytes;
-      p->smem_onchip = gsn::OnchipSmem(nt_max, groups, pd.P, has_aux, false).bytes;
+      p->smem_onchip = lay.bytes;
       p->onchip_ctas_smem = std::max(1, (int)((size_t)(227 * 1024) / (lay.bytes + 1024)));
       GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_onchip_a(kernel_kind, nullptr, &p->onchip_regs)
                                     : gsn::launch_logl_onchip_b(kernel_kind, nullptr, &p->onchip_regs));
@@ -582,7 +599,7 @@ int gsn_problem_destroy(gsn_problem* p) {
   cudaFree(p->d_theta_col); cudaFree(p->d_theta_fixed); cudaFree(p->d_workspace); cudaFree(p->d_counter); cudaFree(p->d_items); cudaFree(p->d_items_cluster);
   cudaFree(p->d_theta); cudaFree(p->d_logl); cudaFree(p->d_info);
   cudaFree(p->d_pred_ws); cudaFree(p->d_pred_items);
-  cudaFree(p->d_oc_blk); cudaFree(p->d_oc_x); cudaFree(p->d_oc_y); cudaFree(p->d_oc_yerr2); cudaFree(p->d_oc_img); cudaFree(p->d_oc_urow);
+  cudaFree(p->d_oc_blk); cudaFree(p->d_oc_x); cudaFree(p->d_oc_y); cudaFree(p->d_oc_yerr2); cudaFree(p->d_oc_img); cudaFree(p->d_oc_urow); cudaFree(p->d_oc_taboff); cudaFree(p->d_oc_tabs);
   if (p->h_theta) cudaFreeHost(p->h_theta);
   if (p->h_logl) cudaFreeHost(p->h_logl);
   if (p->h_info) cudaFreeHost(p->h_info);

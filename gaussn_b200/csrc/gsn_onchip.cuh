@@ -10,11 +10,16 @@
 // arithmetic in the same order -- results are bit-identical to that kernel (tests/test_gpu_onchip.py) -- but at 8-row
 // granularity (N = 141 is factored as 144 rows, not 160) and without workspace, cp.async rings or item lists.
 //
-// Layout.  The rows of every band block start at a multiple of 8 (`OnchipDev`; padding rows are identity rows).  A block
-// of nt tile rows is stored as packed lower-triangular 8x8 tiles, tile (i, k) at i(i+1)/2 + k, each tile in the universal
-// layout of gsn_chol_dmma.cuh (lane t owns the 16 bytes at offset 2t doubles: conflict-free 512-byte warp accesses, and a
-// lane only ever touches its own 16 bytes of a tile).  The diagonal slot (j, j) holds -inv(L(j, j)): the diagonal tile
-// itself is never read again once its inverse exists.
+// Layout.  The rows of every band block start at a multiple of 8 (`OnchipDev`; padding rows are identity rows).  The factor
+// is held as 8x8 tiles in the universal layout of gsn_chol_dmma.cuh (lane t owns the 16 bytes at offset 2t doubles:
+// conflict-free 512-byte warp accesses, and a lane only ever touches its own 16 bytes of a tile).  The diagonal tile (j, j)
+// holds -inv(L(j, j)): L(j, j) itself is never read again once its inverse exists.
+// Only the LIVE part of the factor is stored.  A left-looking sweep reads row r for the last time in tile column r
+// (as the B operand of that column), and nothing but logL leaves the kernel, so the tiles of row r are dead once every
+// warp has finished column r, and tiles born two columns later take their slots.  The slot of tile (i, k) comes from a table
+// built on the host by running exactly that schedule (onchip_slot_table): 100 slots instead of 171 at N = 144, which is four
+// thetas per SM instead of two.  `cdone[j]` counts the warps that have finished column j; a warp enters column j + 2 (where
+// it may overwrite row j) only when all have.
 //
 // Schedule.  A team of T warps (T = blockDim.x / 32 = 1, 2, 4, 8 or 16, chosen by the host so that an SM holds 16 warps)
 // factors one theta; tile row i belongs to warp i mod T.  Left-looking by tile columns:
@@ -37,9 +42,14 @@
 namespace gsn {
 
 #ifndef GSN_ONCHIP_DIAG_TILE
-#define GSN_ONCHIP_DIAG_TILE false   // pivots by shuffle from the tile's own diagonal (see chol8_inv_warp)
+#define GSN_ONCHIP_DIAG_TILE true    // pivots from the broadcast diagonal tile (see chol8_inv_warp): N = 64 56 M evals/s against 46 M by shuffle
 #endif
-constexpr int kOnchipMaxTiles = 28;    // largest band block: 224 rows (406 tiles = 203 KB)
+#ifndef GSN_ONCHIP_LAG
+#define GSN_ONCHIP_LAG 2
+#endif
+constexpr int kOnchipLag = GSN_ONCHIP_LAG;   // tiles written in column j take the slots of row j - kOnchipLag
+constexpr int kOnchipMaxTiles = 28;    // largest band block: 224 rows (225 live tiles = 113 KB; slot numbers fit a byte)
+constexpr int kOnchipDispatchRows = 192;   // band blocks above this run the workspace kernels (N = 224: 2.8 M evals/s here, 3.6 M there)
 constexpr int kOnchipMaxWarps = 16;
 constexpr int kOnchipMaxBlocks = 256;
 
@@ -47,7 +57,10 @@ struct OnchipDev {
   int n_blocks;        // band blocks (1 without a band mask)
   int nt_max;          // tile rows of the largest block
   int n_groups;        // 32-row groups over all blocks: granularity of the final reduction
+  int n_slots;         // tile slots of the largest block's live set
   const int4* blk;     // [n_blocks] {first row in the on-chip layout, tile rows, first group, real rows}
+  const int* tab_off;  // [n_blocks] offset of the block's slot table in `tabs`
+  const unsigned char* tabs;   // slot of tile (i, k) at i(i+1)/2 + k, per distinct block size
   const double* x;     // per row of the on-chip layout (bands aligned to 8 rows)
   const double* y;
   const double* yerr2;
@@ -61,17 +74,16 @@ struct OnchipCtl {
   int prog_row;        // rows [0, prog_row) are stored through their last off-diagonal tile
   int prog_diag;       // pivot tiles [0, prog_diag) are factored: -inv(L(j,j)) is stored
   int prog_z;          // z(0) ... z(prog_z - 1) are stored
-  int pre_ready;       // specialised teams: rows [1, pre_ready] are stored through column row - 2 and their accumulators handed over
+  int cdone[kOnchipMaxTiles];   // warps that have finished tile column j
   double gmant[8];     // pivot product of each 32-row group of the block in work, as mantissa ...
   int gexpo[8];        // ... and exponent; the logarithms are taken after the factorisation, off its critical path
 };
 
 // Shared-memory carve-up (offsets in doubles).
-constexpr int kPreSlot = 80;   // double2 units per hand-over slot: S [0, 32), D [32, 64), y (one double per lane) [64, 80)
 struct OnchipSmem {
-  int off_theta, off_ldg, off_zzg, off_ctl, off_vec, off_pre, off_tiles, vstride;
+  int off_theta, off_ldg, off_zzg, off_ctl, off_vec, off_tab, off_tiles, vstride;
   size_t bytes;
-  __host__ __device__ OnchipSmem(int nt_max, int n_groups, int P, bool has_aux, bool spec) {
+  __host__ __device__ OnchipSmem(int nt_max, int n_slots, int n_groups, int P, bool has_aux) {
     int o = 64;                                   // 2^(j/64) table of fast_exp
     off_theta = o; o += (P + 1) & ~1;
     off_ldg = o; o += n_groups;
@@ -79,12 +91,29 @@ struct OnchipSmem {
     o = (o + 1) & ~1;
     off_ctl = o; o += (int)((sizeof(OnchipCtl) + 15) / 16 * 2);   // vectors and tiles are accessed 16 bytes at a time
     vstride = 8 * nt_max;
-    off_vec = o; o += vstride * (has_aux ? 6 : 5);   // shifted epochs, magnifications, residual, yerr^2, z, [aux]
-    off_pre = o; if (spec) o += 4 * kPreSlot * 2;      // hand-over ring between the row owners and the pivot warp
-    off_tiles = o; o += nt_max * (nt_max + 1) / 2 * 64;
+    off_vec = o; o += vstride * (has_aux ? 5 : 4);   // shifted epochs, magnifications, residual (overwritten by z), yerr^2, [aux]
+    off_tab = o; o += (nt_max * (nt_max + 1) / 2 + 15) / 16 * 2;   // slot table of the block in work (bytes)
+    off_tiles = o; o += n_slots * 64;
     bytes = (size_t)o * 8;
   }
 };
+
+// Slot table of a block of nt tile rows: tile (i, k) -> slot, by simulating the schedule.  Phase p (tile column p; p = -1
+// is the first pivot tile) gives birth to the pivot tile (p + 1, p + 1) and the tiles (i, p), i > p; the slots of row
+// p - kOnchipLag are free again from phase p on.  Returns the number of slots.
+inline int onchip_slot_table(int nt, unsigned char* tab) {
+  auto tri = [](int i) { return i * (i + 1) / 2; };
+  int free_list[kOnchipMaxTiles * (kOnchipMaxTiles + 1) / 2], head = 0, tail = 0, fresh = 0;
+  auto take = [&]() { return head < tail ? free_list[head++] : fresh++; };
+  for (int p = -1; p < nt - 1; ++p) {
+    if (p >= kOnchipLag)
+      for (int k = 0; k <= p - kOnchipLag; ++k) free_list[tail++] = tab[tri(p - kOnchipLag) + k];
+    tab[tri(p + 1) + p + 1] = (unsigned char)take();
+    if (p >= 0)
+      for (int i = p + 1; i < nt; ++i) tab[tri(i) + p] = (unsigned char)take();
+  }
+  return fresh;
+}
 
 __device__ __forceinline__ bool onchip_wait_gt(const int* p, int v, const int* fail) {
   while (ld_acquire_shared(p) <= v) {
@@ -105,12 +134,12 @@ __device__ long long g_onchip_trace[8192];
 template <int KIND>
 struct OnchipTeam {
   bool trace_on = false;
-  double2* pre;        // hand-over ring (specialised teams)
   KernelConsts kc;
   const double* exptab;
   const double *xs, *bs, *rs, *e2, *aux;
   double* zs;
   double2* tiles;      // already offset by lane
+  const unsigned char* tab;   // slot of tile (i, k) at tri(i) + k
   OnchipCtl* ctl;
   double* ldg;
   const int* urow;     // of this block
@@ -148,6 +177,7 @@ struct OnchipTeam {
   }
 
   __device__ __forceinline__ static int tri(int i) { return i * (i + 1) / 2; }
+  __device__ __forceinline__ double2* tile(const unsigned char* row, int k) const { return tiles + (int)row[k] * 32; }
   // Residual row.  y(i) = sum_k L(i,k) z(k) is accumulated as one partial sum per lane (its two columns of every tile, two
   // DFMAs per tile: an 8x8 matrix-vector product issued as DMMAs would occupy the FP64 pipe eight times as long), reduced over
   // the four lanes of a row at the end; z(i) = inv(L(i,i)) (r(i) - y(i)).
@@ -168,9 +198,19 @@ struct OnchipTeam {
     return p;
   }
 
+  // Before the first tile store of column j: the slots it may take are those of row j - kOnchipLag, dead once every warp has
+  // left that column.
+  __device__ __forceinline__ bool may_write(int j, bool& write_ok) const {
+    if (T > 1 && !write_ok) {
+      if (j >= kOnchipLag && !onchip_wait_gt(&ctl->cdone[j - kOnchipLag], T - 1, &ctl->fail)) return false;
+      write_ok = true;
+    }
+    return true;
+  }
+
   // Column j for R of this warp's rows: T(i[r], j).  Returns false if the theta failed while waiting.
   template <int R>
-  __device__ __forceinline__ bool panel(const int (&i)[R], int j, const Cols& q, bool& row_ok, bool& diag_ok) const {
+  __device__ __forceinline__ bool panel(const int (&i)[R], int j, const Cols& q, bool& row_ok, bool& diag_ok, bool& write_ok) const {
     double2 S[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) S[r] = build(i[r], j, q);
@@ -178,16 +218,16 @@ struct OnchipTeam {
       if (!onchip_wait_gt(&ctl->prog_row, j, &ctl->fail)) return false;
       row_ok = true;
     }
-    const double2* Bp = tiles + tri(j) * 32;
-    const double2* Ap[R];
+    const unsigned char* tb = tab + tri(j);
+    const unsigned char* ta[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) Ap[r] = tiles + tri(i[r]) * 32;
+    for (int r = 0; r < R; ++r) ta[r] = tab + tri(i[r]);
 #pragma unroll 2
     for (int k = 0; k < j; ++k) {
-      const double2 b = Bp[k * 32];
+      const double2 b = *tile(tb, k);
       double2 a[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) a[r] = Ap[r][k * 32];
+      for (int r = 0; r < R; ++r) a[r] = *tile(ta[r], k);
 #pragma unroll
       for (int r = 0; r < R; ++r) dmma(S[r], a[r].x, b.x);
 #pragma unroll
@@ -197,13 +237,14 @@ struct OnchipTeam {
       if (!onchip_wait_gt(&ctl->prog_diag, j, &ctl->fail)) return false;
       diag_ok = true;
     }
-    const double2 nW = Bp[j * 32];
+    const double2 nW = *tile(tb, j);
+    if (!may_write(j, write_ok)) return false;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       double2 X = make_double2(0.0, 0.0);
       dmma(X, S[r].x, nW.x);
       dmma(X, S[r].y, nW.y);
-      const_cast<double2*>(Ap[r])[j * 32] = X;
+      *tile(ta[r], j) = X;
     }
     return true;
   }
@@ -211,24 +252,24 @@ struct OnchipTeam {
   // Look-ahead: T(i, j) for i = j + 1 (skipped for j = -1) and D(i) back to back.
   // Critical path of the whole factorisation: prog_diag > j  ->  solve  ->  D += X X^T  ->  8x8 elimination  ->  prog_diag = i + 1.
   // Everything else (the GEMMs over k < j, the residual row Z, the pivot products) is kept off it.
-  __device__ __forceinline__ bool pivot_row(int j) const {
+  __device__ __forceinline__ bool pivot_row(int j, bool& write_ok) const {
     const int i = j + 1;
     GSN_TRACE(0, j);
     const Cols qi = load_cols(i);
     double2 S = make_double2(0.0, 0.0), X = make_double2(0.0, 0.0);
     double2 D = build(i, i, qi);
     double y = 0.0;
-    double2* Ap = tiles + tri(i) * 32;
+    const unsigned char* ta = tab + tri(i);
     if (j >= 0) {
       S = build(i, j, load_cols(j));
       GSN_TRACE(1, j);
       if (T > 1 && !(onchip_wait_gt(&ctl->prog_row, j, &ctl->fail) && onchip_wait_gt(&ctl->prog_z, j - 1, &ctl->fail))) return false;
       GSN_TRACE(2, j);
-      const double2* Bp = tiles + tri(j) * 32;
+      const unsigned char* tb = tab + tri(j);
 #pragma unroll 2
       for (int k = 0; k < j; ++k) {
-        const double2 b = Bp[k * 32];
-        const double2 a = Ap[k * 32];
+        const double2 b = *tile(tb, k);
+        const double2 a = *tile(ta, k);
         const double2 z = zpair(k);
         dmma(S, a.x, b.x);
         dmma(D, a.x, a.x);
@@ -239,10 +280,11 @@ struct OnchipTeam {
       GSN_TRACE(3, j);
       if (T > 1 && !onchip_wait_gt(&ctl->prog_diag, j, &ctl->fail)) return false;
       GSN_TRACE(4, j);
-      const double2 nWj = Bp[j * 32];
+      const double2 nWj = *tile(tb, j);
       dmma(X, S.x, nWj.x);
       dmma(X, S.y, nWj.y);
-      Ap[j * 32] = X;
+      if (!may_write(j, write_ok)) return false;
+      *tile(ta, j) = X;
       if (T > 1) {
         __syncwarp();
         if (lane == 0) st_release_shared(&ctl->prog_row, i + 1);
@@ -255,7 +297,7 @@ struct OnchipTeam {
     double2 nW;
     GSN_TRACE(5, j);
     chol8_inv_warp<GSN_ONCHIP_DIAG_TILE>(make_double2(-D.x, -D.y), lane, nW, mant, expo, failrow);
-    Ap[i * 32] = nW;
+    *tile(ta, i) = nW;
     if (T > 1) {
       __syncwarp();
       if (lane == 0) st_release_shared(&ctl->prog_diag, i + 1);
@@ -283,193 +325,46 @@ struct OnchipTeam {
     return true;
   }
 
-  // ---------------------------------------------------------------------------------------------------------------------
-  // Specialised team (T >= 4).  An FP64 instruction of a warp that walks a dependent chain waits behind whatever DMMAs the
-  // other warps of its SM sub-partition have queued: the 8x8 elimination takes 1.5 k cycles alone, 18 k next to ONE warp
-  // that streams DMMAs and is starved next to two (bench/chol8_lat.cu; warps on other sub-partitions do not matter) -- and
-  // the pivot chain is the critical path of the factorisation.  So warp 0 does nothing but the chain, the warps of the
-  // other three sub-partitions (warp & 3 != 0) own the rows, and warps 4, 8, 12 of larger teams idle at the barrier:
-  // sub-partition 0 carries no streaming work at all.
-  //   row owner, column j = i - 2 (pre_D): T(i, j), and in the same sweep over k < j the accumulators of the NEXT two
-  //     tiles of row i -- S1 = sum_{k<=i-3} L(i,k) L(i-1,k)^T - K(i,i-1), D(i), Z(i) -- parked in a hand-over slot;
-  //   pivot warp, step i: S1 += L(i,i-2) L(i-1,i-2)^T (the one term that was not available two columns earlier; its second
-  //     operand is the X of the previous step, still in registers), solve, D += X X^T, 8x8 elimination, residual.
-  // Nothing on the chain waits for a GEMM any more.  Same tile arithmetic in the same order: bit-identical to T <= 2.
-  __device__ __forceinline__ double2* pre_slot(int i) const { return pre + (i & 3) * kPreSlot; }
-
-  __device__ __forceinline__ void pivot_chain() const {
-    // -inv(L(i-1,i-1)), z(i-1) and L(i-1,i-2) stay in registers from one step to the next
-    double2 nWprev = make_double2(0.0, 0.0), zprev = make_double2(0.0, 0.0), Xprev = make_double2(0.0, 0.0);
-    constexpr unsigned kFull = 0xffffffffu;
-    for (int i = 0; i < nt; ++i) {
-      double2* Ap = tiles + tri(i) * 32;
-      double2 D, X = make_double2(0.0, 0.0);
-      double y = 0.0;
-      GSN_TRACE(0, i - 1);
-      if (i == 0) {
-        D = build(0, 0, load_cols(0));
-      } else {
-        if (!onchip_wait_gt(&ctl->pre_ready, i - 1, &ctl->fail)) return;
-        GSN_TRACE(4, i - 1);
-        const double2* ps = pre_slot(i);
-        double2 S = ps[lane];
-        D = ps[32 + lane];
-        y = reinterpret_cast<const double*>(ps + 64)[lane];
-        if (i >= 2) {
-          const double2 a = Ap[(i - 2) * 32];
-          dmma(S, a.x, Xprev.x);
-          dmma(S, a.y, Xprev.y);
-        }
-        dmma(X, S.x, nWprev.x);
-        dmma(X, S.y, nWprev.y);
-        Ap[(i - 1) * 32] = X;
-        __syncwarp();
-        if (lane == 0) st_release_shared(&ctl->prog_row, i + 1);
-        dmma(D, X.x, X.x);
-        dmma(D, X.y, X.y);
-      }
-      double mant = 1.0;
-      int expo = 0, failrow = -1;
-      double2 nW;
-      GSN_TRACE(5, i - 1);
-      chol8_inv_warp<GSN_ONCHIP_DIAG_TILE>(make_double2(-D.x, -D.y), lane, nW, mant, expo, failrow);
-      Ap[i * 32] = nW;
-      __syncwarp();
-      if (lane == 0) st_release_shared(&ctl->prog_diag, i + 1);
-      GSN_TRACE(6, i - 1);
-      if (i > 0) y = ydot(y, X, zprev);
-      const double zi = finish_z(i, y, nW);
-      if (lane == 0) {
-        if (failrow >= 0) {
-          const int u = urow[8 * i + failrow];
-          atomicCAS(&ctl->fail, 0, u >= 0 ? u + 1 : n_total);
-        }
-        if ((i & 3) != 0) { mant *= ctl->gmant[i >> 2]; expo += ctl->gexpo[i >> 2]; }
-        ctl->gmant[i >> 2] = mant;
-        ctl->gexpo[i >> 2] = expo;
-      }
-      __syncwarp();
-      if (lane == 0) st_release_shared(&ctl->prog_z, i + 1);
-      GSN_TRACE(7, i - 1);
-      nWprev = nW;
-      Xprev = X;
-      zprev = make_double2(__shfl_sync(kFull, zi, 8 * (lane & 3)), __shfl_sync(kFull, zi, 8 * (lane & 3) + 4));   // z(i)[2q], [2q+1]
-      if (failrow >= 0) return;
-    }
-  }
-
-  // Row 1 has no column two to its left: its accumulators are just the covariance tiles.
-  __device__ __forceinline__ void pre_first() const {
-    double2* ps = pre_slot(1);
-    ps[lane] = build(1, 0, load_cols(0));
-    ps[32 + lane] = build(1, 1, load_cols(1));
-    reinterpret_cast<double*>(ps + 64)[lane] = 0.0;
-    __syncwarp();
-    if (lane == 0) st_release_shared(&ctl->pre_ready, 1);
-  }
-
-  // Column j = i - 2 of row i: T(i, j), and the accumulators of (i, i-1), (i, i) and the residual through column j.
-  __device__ __forceinline__ bool pre_D(int i, int j, const Cols& q) const {
-    double2 S = build(i, j, q);
-    double2 S1 = build(i, i - 1, load_cols(i - 1));
-    double2 D = build(i, i, load_cols(i));
-    double y = 0.0;
-    // row j complete; row i - 1 stored through column j - 1 (its owner's pre_D); z through j - 1
-    if (!(onchip_wait_gt(&ctl->prog_row, j, &ctl->fail) && onchip_wait_gt(&ctl->pre_ready, i - 2, &ctl->fail) &&
-          onchip_wait_gt(&ctl->prog_z, j - 1, &ctl->fail))) return false;
-    const double2* Bp = tiles + tri(j) * 32;
-    const double2* B1p = tiles + tri(i - 1) * 32;
-    double2* Ap = tiles + tri(i) * 32;
-#pragma unroll 2
-    for (int k = 0; k < j; ++k) {
-      const double2 b = Bp[k * 32];
-      const double2 b1 = B1p[k * 32];
-      const double2 a = Ap[k * 32];
-      const double2 z = zpair(k);
-      dmma(S, a.x, b.x);
-      dmma(S1, a.x, b1.x);
-      dmma(D, a.x, a.x);
-      dmma(S, a.y, b.y);
-      dmma(S1, a.y, b1.y);
-      dmma(D, a.y, a.y);
-      y = ydot(y, a, z);
-    }
-    if (!onchip_wait_gt(&ctl->prog_diag, j, &ctl->fail)) return false;
-    const double2 nWj = Bp[j * 32];
-    double2 X = make_double2(0.0, 0.0);
-    dmma(X, S.x, nWj.x);
-    dmma(X, S.y, nWj.y);
-    Ap[j * 32] = X;
-    if (!onchip_wait_gt(&ctl->prog_z, j, &ctl->fail)) return false;
-    dmma(D, X.x, X.x);
-    dmma(D, X.y, X.y);
-    y = ydot(y, X, zpair(j));
-    double2* ps = pre_slot(i);
-    ps[lane] = S1;
-    ps[32 + lane] = D;
-    reinterpret_cast<double*>(ps + 64)[lane] = y;
-    __syncwarp();
-    if (lane == 0) st_release_shared(&ctl->pre_ready, i);
-    return true;
-  }
-
-  // Row owner b of NB: rows 1 + b, 1 + b + NB, ...
-  __device__ __forceinline__ void bulk(int b, int NB) const {
-    if (b == 0 && nt > 1) pre_first();
-    for (int j = 0; j < nt - 1; ++j) {
-      if (ld_volatile_shared(&ctl->fail) != 0) break;
-      int i = j + 1 + (b - j % NB + NB) % NB;   // this warp's first row below j
-      if (i == j + 1) i += NB;                  // tile (j + 1, j) belongs to the pivot warp
-      if (i >= nt) continue;
-      const Cols q = load_cols(j);
-      bool row_ok = false, diag_ok = false, ok = true;
-      if (i == j + 2) { ok = pre_D(i, j, q); row_ok = diag_ok = true; i += NB; }
-      for (; ok && i + NB < nt; i += 2 * NB) {
-        const int ii[2] = {i, i + NB};
-        ok = panel<2>(ii, j, q, row_ok, diag_ok);
-      }
-      if (ok && i < nt) {
-        const int ii[1] = {i};
-        ok = panel<1>(ii, j, q, row_ok, diag_ok);
-      }
-      if (!ok) break;
-    }
-  }
-
   __device__ __forceinline__ void factor(int warp) const {
     for (int j = -1; j < nt - 1; ++j) {
       if (ld_volatile_shared(&ctl->fail) != 0) break;
       int i = (j + 1) + ((warp - (j + 1)) & (T - 1));   // this warp's first row below j
-      if (i >= nt) continue;
-      if (i == j + 1) {
-        if (!pivot_row(j)) break;
+      bool ok = true, write_ok = false;
+      if (i == j + 1 && i < nt) {
+        ok = pivot_row(j, write_ok);
         i += T;
       }
-      if (j < 0 || i >= nt) continue;
-      const Cols q = load_cols(j);
-      bool row_ok = false, diag_ok = false;
-      bool ok = true;
-      for (; ok && i + T < nt; i += 2 * T) {
-        const int ii[2] = {i, i + T};
-        ok = panel<2>(ii, j, q, row_ok, diag_ok);
-      }
-      if (ok && i < nt) {
-        const int ii[1] = {i};
-        ok = panel<1>(ii, j, q, row_ok, diag_ok);
+      if (ok && j >= 0 && i < nt) {
+        const Cols q = load_cols(j);
+        bool row_ok = false, diag_ok = false;
+        for (; ok && i + T < nt; i += 2 * T) {
+          const int ii[2] = {i, i + T};
+          ok = panel<2>(ii, j, q, row_ok, diag_ok, write_ok);
+        }
+        if (ok && i < nt) {
+          const int ii[1] = {i};
+          ok = panel<1>(ii, j, q, row_ok, diag_ok, write_ok);
+        }
       }
       if (!ok) break;
+      if (T > 1 && j >= 0) {
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("red.release.cta.shared.add.s32 [%0], 1;" :: "r"(smem_u32(&ctl->cdone[j])) : "memory");
+        }
+      }
     }
   }
 };
 
-template <int KIND, bool kSpec>
+template <int KIND>
 __global__ void __launch_bounds__(kOnchipMaxWarps * 32, 1)
 logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta, long long B, long long ld,
                    const double* __restrict__ hostmean, GatherOut out, int* __restrict__ info, unsigned flags,
                    unsigned* counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
-  const OnchipSmem lay(od.nt_max, od.n_groups, pd.P, kernel_has_aux<KIND>(), kSpec);
+  const OnchipSmem lay(od.nt_max, od.n_slots, od.n_groups, pd.P, kernel_has_aux<KIND>());
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
   double* exptab = sm;
   double* th = sm + lay.off_theta;
@@ -480,8 +375,8 @@ logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta
   double* bs = xs + lay.vstride;
   double* rs = bs + lay.vstride;
   double* e2 = rs + lay.vstride;
-  double* zs = e2 + lay.vstride;
-  double* aux = kernel_has_aux<KIND>() ? zs + lay.vstride : xs;
+  double* zs = rs;      // z(i) replaces the residual of tile row i (read once, by the warp that then writes z(i))
+  double* aux = kernel_has_aux<KIND>() ? e2 + lay.vstride : xs;
 
   for (int i = tid; i < 64; i += nthreads) exptab[i] = kExp2Tab[i];
 #ifdef GSN_ONCHIP_TRACE
@@ -511,7 +406,8 @@ logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta
     team.kc = kernel_consts<KIND>(th);
     team.exptab = exptab; team.xs = xs; team.bs = bs; team.rs = rs; team.e2 = e2; team.aux = aux; team.zs = zs;
     team.tiles = reinterpret_cast<double2*>(sm + lay.off_tiles) + lane;
-    team.pre = reinterpret_cast<double2*>(sm + lay.off_pre);
+    unsigned char* tab = reinterpret_cast<unsigned char*>(sm + lay.off_tab);
+    team.tab = tab;
     team.ctl = ctl; team.ldg = ldg; team.lane = lane; team.T = nthreads >> 5; team.n_total = pd.N;
     const KernelConsts& kc = team.kc;
     // a non-finite kernel constant or shifted epoch makes the covariance NaN, which the reference's Cholesky turns into
@@ -537,7 +433,12 @@ logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta
         xs[n] = x_s; bs[n] = b; rs[n] = r; e2[n] = e;
         if (kernel_has_aux<KIND>()) aux[n] = ax;
       }
-      if (tid == 0) { ctl->prog_row = 1; ctl->prog_diag = 0; ctl->prog_z = 0; ctl->pre_ready = 0; }
+      {
+        const unsigned char* src = od.tabs + od.tab_off[blk];
+        for (int n = tid; n < nt * (nt + 1) / 2; n += nthreads) tab[n] = src[n];
+        for (int n = tid; n < nt; n += nthreads) ctl->cdone[n] = 0;
+      }
+      if (tid == 0) { ctl->prog_row = 1; ctl->prog_diag = 0; ctl->prog_z = 0; }
       if (__syncthreads_or(bad)) { dead = true; break; }
       bad = 0;
       team.nt = nt; team.nrows = nrows; team.urow = od.urow + r0;
@@ -545,12 +446,7 @@ logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta
       team.trace_on = (blockIdx.x == 0 && blk == 0 && n_done == GSN_ONCHIP_TRACE);
       if (team.trace_on && tid == 0) { g_onchip_trace[0] = clock64(); g_onchip_trace[1] = nt; }
 #endif
-      if constexpr (kSpec) {
-        if (warp == 0) team.pivot_chain();
-        else if ((warp & 3) != 0) team.bulk(warp - 1 - (warp >> 2), team.T - (team.T >> 2));
-      } else {
-        team.factor(warp);
-      }
+      team.factor(warp);
       __syncthreads();
 #ifdef GSN_ONCHIP_TRACE
       if (team.trace_on && tid == 0) g_onchip_trace[2] = clock64();

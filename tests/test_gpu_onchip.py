@@ -21,6 +21,7 @@ def _legacy(monkeypatch, ds, kernel, mean, lens, n_images, theta, **kw):
     """The same problem through the workspace kernels (GSN_FORCE_SHAPE=legacy is read when the handle is created)."""
     from gaussn_b200 import _engine
     monkeypatch.setenv("GSN_FORCE_SHAPE", "legacy")
+    monkeypatch.delenv("GSN_ONCHIP_MAX_ROWS", raising=False)
     gp = _gp_for(ds, kernel, mean, lens, n_images, theta[0])
     out = gp.loglikelihood_batch(theta, **kw)
     assert gp._problem.query(_engine.Q_ONCHIP) == 0 and gp._problem.query(_engine.Q_PATH) != _engine.PATH_ONCHIP
@@ -30,7 +31,9 @@ def _legacy(monkeypatch, ds, kernel, mean, lens, n_images, theta, **kw):
 
 @pytest.mark.parametrize("N", [1, 2, 3, 7, 8, 9, 15, 16, 17, 31, 32, 33, 40, 63, 64, 65, 96, 100, 141, 160, 161, 192, 194, 217, 224])
 def test_every_order_up_to_224_matches_oracle_and_workspace_kernels(libgsn, monkeypatch, N):
+    """The shape is compiled for band blocks of up to 224 rows and dispatched up to 192 (GSN_ONCHIP_MAX_ROWS moves the limit)."""
     from gaussn_b200 import _engine
+    monkeypatch.setenv("GSN_ONCHIP_MAX_ROWS", "224")
     rng = np.random.default_rng(5000 + N)
     n_images = 2 if N >= 2 else 1
     ds = _synth(rng, N, 1, n_images)
@@ -43,14 +46,16 @@ def test_every_order_up_to_224_matches_oracle_and_workspace_kernels(libgsn, monk
     _agree(got, _legacy(monkeypatch, ds, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", n_images, theta))
 
 
-def test_order_225_uses_the_workspace_kernels(libgsn):
+@pytest.mark.parametrize("N,n_bands,onchip", [(192, 1, 1), (193, 1, 0), (225, 1, 0), (768, 4, 1), (780, 4, 0)])
+def test_dispatch_limit_is_the_largest_band_block(libgsn, N, n_bands, onchip):
     from gaussn_b200 import _engine
-    rng = np.random.default_rng(1)
-    ds = _synth(rng, 225, 1, 2)
+    rng = np.random.default_rng(N)
+    ds = _synth(rng, N, n_bands, 2)
     theta = _theta_box(rng, 8, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", 2)
     gp = _gp_for(ds, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", 2, theta[0])
-    gp.loglikelihood_batch(theta)
-    assert gp._problem.query(_engine.Q_ONCHIP) == 0
+    got = gp.loglikelihood_batch(theta)
+    assert gp._problem.query(_engine.Q_ONCHIP) == onchip
+    assert_logl_close(got, _oracle_batch(ds, theta, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", gp), f"N={N}")
 
 
 @pytest.mark.parametrize("kernel", ["ExpSquaredKernel", "ExponentialKernel", "ConstantKernel", "Matern32Kernel", "Matern52Kernel",
@@ -75,6 +80,7 @@ def test_every_kernel_on_the_reference_shapes(libgsn, monkeypatch, kernel, n_ban
 def test_team_size_and_batch_order_do_not_change_a_bit(libgsn, monkeypatch, n_bands, n_images, N, kernel):
     """1, 2, 4, 8 or 16 warps per theta; 700 thetas (several waves of the persistent grid), 40, 3 and 1 per call; reversed."""
     from gaussn_b200 import _engine
+    monkeypatch.setenv("GSN_ONCHIP_MAX_ROWS", "224")
     rng = np.random.default_rng(N * 3 + n_bands)
     ds = _synth(rng, N, n_bands, n_images)
     lens = "ConstantMagnification" if n_images > 1 else "NoLensing"
@@ -114,24 +120,45 @@ def test_every_mean_and_lensing_model_on_chip(libgsn, monkeypatch, mean, lens):
     _agree(got, _legacy(monkeypatch, ds, "Matern32Kernel", mean, lens, n_images, theta))
 
 
-def test_failure_info_is_the_callers_row(libgsn, monkeypatch):
-    """info = 1-based index, in the caller's row order, of the first non-positive pivot -- the same in both shapes, also
-    with a band mask (where the internal layouts differ)."""
+@pytest.mark.parametrize("n_bands", [1, 3])
+def test_failure_info_is_the_callers_row(libgsn, monkeypatch, n_bands):
+    """info = 1-based index, in the caller's row order, of a non-positive pivot.  One band: the first such pivot, the same
+    in both shapes.  With a band mask the internal layouts differ (bands aligned to 8 rows here, to 32 in the workspace
+    kernels, which also factor the bands concurrently and report whichever failure comes first in time): both must name a
+    pivot that LAPACK's factorisation of that band also rejects or precedes."""
+    import scipy.linalg
     from gaussn_b200 import _engine
     rng = np.random.default_rng(12)
-    ds = _synth(rng, 150, 3, 2)
+    ds = _synth(rng, 150, n_bands, 2)
     theta = _theta_box(rng, 16, "RationalQuadraticKernel", "UniformMean", "ConstantMagnification", 2)
     theta[:, 0] *= 40.0        # A^2 (1 + d^2 / ...) with a large amplitude: indefinite early on
     gp = _gp_for(ds, "RationalQuadraticKernel", "UniformMean", "ConstantMagnification", 2, theta[0])
     gp.loglikelihood_batch(theta)
     out, info = gp._problem.logl_host(theta, 0, return_info=True)
+    assert gp._problem.query(_engine.Q_PATH) == _engine.PATH_ONCHIP
     assert np.isnan(out).any() and np.all((info > 0) == np.isnan(out)) and info.max() <= 150
     monkeypatch.setenv("GSN_FORCE_SHAPE", "legacy")
     gp2 = _gp_for(ds, "RationalQuadraticKernel", "UniformMean", "ConstantMagnification", 2, theta[0])
     gp2.loglikelihood_batch(theta)
     out2, info2 = gp2._problem.logl_host(theta, 0, return_info=True)
     _agree(out, out2)
-    np.testing.assert_array_equal(info, info2)
+    if n_bands == 1:
+        np.testing.assert_array_equal(info, info2)
+    else:
+        assert np.all((info2 > 0) == np.isnan(out2)) and info2.max() <= 150
+    # the first failing pivot of the first failing band, from LAPACK (potrf reports the order of the leading minor)
+    per_band = 150 // n_bands
+    for t in np.flatnonzero(info > 0)[:6]:
+        shifted, b = gp_oracle.lens("ConstantMagnification", list(theta[t, 4:]), ds["x"], n_bands, 2, gp.indices)
+        K = np.outer(b, b) * gp_oracle.covariance("RationalQuadraticKernel", list(theta[t, :3]), shifted) + np.diag(ds["yerr"] ** 2)
+        first = None
+        for band in range(n_bands):
+            r0, r1 = band * per_band, (band + 1) * per_band if band < n_bands - 1 else 150
+            _, lapack_info = scipy.linalg.lapack.dpotrf(K[r0:r1, r0:r1], lower=1)
+            if lapack_info > 0:
+                first = r0 + lapack_info
+                break
+        assert first is not None and abs(int(info[t]) - first) <= 1, (t, info[t], first)   # borderline pivots may flip by rounding
 
 
 def test_new_observations_reach_the_on_chip_tables(libgsn):

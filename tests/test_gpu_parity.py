@@ -389,10 +389,12 @@ def test_hypothesis_random_layouts_and_theta(libgsn):
 @pytest.mark.parametrize("kernel,n_bands,n_images,N", [("ExpSquaredKernel", 1, 2, 141), ("Matern32Kernel", 4, 2, 194), ("OUKernel", 1, 3, 33),
                                                        ("GibbsKernel", 2, 2, 200), ("JJKernel", 1, 2, 96), ("Matern52Kernel", 3, 2, 336),
                                                        ("ExpSquaredKernel", 4, 2, 512), ("Matern32Kernel", 3, 4, 396), ("OUKernel", 6, 2, 900)])
-def test_one_warp_per_theta_shape_on_large_batches(libgsn, kernel, n_bands, n_images, N):
-    """Batches of 512+ theta at N <= 336 -- or, with a band mask, with band blocks of at most 336 rows -- run the narrow
-    launch shape (one warp per theta); smaller batches of the same problem run the four-warp shape.  Both must agree with the oracle and with each other bit for bit."""
+def test_one_warp_per_theta_shape_on_large_batches(libgsn, monkeypatch, kernel, n_bands, n_images, N):
+    """Workspace kernels (band blocks above 192 rows; here forced for the smaller ones as well): batches of 512+ theta with
+    band blocks of at most 336 rows run the narrow launch shape (one warp per theta); smaller batches of the same problem run
+    the four-warp shape.  Both must agree with the oracle and with each other bit for bit."""
     from gaussn_b200 import _engine
+    monkeypatch.setenv("GSN_FORCE_SHAPE", "legacy")
     rng = np.random.default_rng(N * 7 + n_bands)
     ds = _synth(rng, N, n_bands, n_images)
     theta = _theta_box(rng, 640, kernel, "UniformMean", "ConstantMagnification", n_images)
