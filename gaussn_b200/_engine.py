@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "gsn_mean", "gsn_lens", "gsn_kernel_nparams", "gsn_mean_nparams", "gsn_lens_nparams",
     "gsn_abi_version", "gsn_last_error", "gsn_item_order", "gsn_logl_batch_gather",
     "gsn_predict_batch", "gsn_predict_batch_host", "gsn_predict_item_order", "gsn_problem_set_data",
+    "gsn_measure_fp64_peak", "gsn_device_count",
 )
 MAX_ORDER = 8128   # largest padded order of a factorisation (32 * 254 block rows), also for n_rows + M of a prediction
 
@@ -86,6 +87,8 @@ def load():
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.gsn_predict_batch_host.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _dp, C.c_int64,
                                                _dp, _dp, _dp, _dp, _ip]
+        lib.gsn_device_count.restype = C.c_int32
+        lib.gsn_measure_fp64_peak.argtypes = [C.c_int, C.c_double, _dp]
         lib.gsn_query.argtypes = [C.c_void_p, C.c_int32]
         lib.gsn_query.restype = C.c_int64
         lib.gsn_covariance.argtypes = [C.c_int, C.c_int32, _dp, C.c_int32, _dp, C.c_int64, _dp, C.c_int64, _dp]
@@ -118,7 +121,22 @@ def _ptr(a: np.ndarray):
 
 
 def default_device() -> int:
-    return int(os.environ.get("LOCAL_RANK", os.environ.get("GSN_DEVICE", "0")))
+    """Device used when none is given: GSN_DEVICE if set; else LOCAL_RANK (torchrun) folded onto the devices this process
+    can see (launchers that expose one GPU per rank through CUDA_VISIBLE_DEVICES leave every rank with device 0); else 0."""
+    if os.environ.get("GSN_DEVICE"):
+        return int(os.environ["GSN_DEVICE"])
+    rank = os.environ.get("LOCAL_RANK")
+    if rank:
+        n = int(load().gsn_device_count())
+        return int(rank) % n if n > 0 else int(rank)
+    return 0
+
+
+def measure_fp64_peak(device=None, seconds=0.3) -> float:
+    """FP64 tensor-pipe rate of the device in TFLOP/s (independent DMMA chains on every SM)."""
+    out = C.c_double(0.0)
+    _check(load().gsn_measure_fp64_peak(default_device() if device is None else device, float(seconds), C.byref(out)))
+    return float(out.value)
 
 
 # --- single-call plugin evaluations ----------------------------------------

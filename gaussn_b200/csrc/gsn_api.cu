@@ -225,6 +225,23 @@ __global__ void lens_kernel(int kind, const double* __restrict__ lp, const int* 
   }
 }
 
+// FP64 tensor-pipe peak, measured: eight independent DMMA accumulator chains per warp, 32 warps per SM (the configuration
+// that gave the highest rate in bench/peaks.cu).  Used by bench.py --peaks to re-measure the roofline denominator in-run.
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+  double2 acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = make_double2(threadIdx.x * 1e-3 + i, 1.0);
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * blockIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gsn::dmma(acc[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i].x + acc[i].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int check_indices(const int64_t* indices, int32_t n_bands, int32_t n_images, int64_t N) {
   if (!indices) return fail(GSN_ERR_INVALID, "indices is null");
   const int64_t S = (int64_t)n_bands * n_images;
@@ -335,6 +352,10 @@ struct DevBuf {
 extern "C" {
 
 int32_t gsn_abi_version(void) { return GSN_ABI_VERSION; }
+int32_t gsn_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 const char* gsn_last_error(void) { return g_last_error.c_str(); }
 int32_t gsn_kernel_nparams(int32_t kind) { return gsn::kernel_nparams(kind); }
 int32_t gsn_mean_nparams(int32_t kind) { return gsn::mean_nparams(kind); }
@@ -889,6 +910,45 @@ int64_t gsn_predict_item_order(int64_t n_rows, int64_t M, int32_t want_cov, uint
   return n;
 }
 
+static int open_device(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(GSN_ERR_CUDA, "no CUDA device available; libgsn has no CPU path");
+  if (device < 0 || device >= ndev) return fail(GSN_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+  return GSN_OK;
+}
+
+int gsn_measure_fp64_peak(int device, double seconds, double* tflops_out) {
+  if (!tflops_out) return fail(GSN_ERR_INVALID, "tflops_out is null");
+  if (int rc = open_device(device)) return rc;
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  GSN_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 4, threads = 256;
+  DevBuf out;
+  GSN_CUDA(out.alloc(sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  GSN_CUDA(cudaEventCreate(&e0));
+  GSN_CUDA(cudaEventCreate(&e1));
+  int iters = 20000;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {      // the first pass calibrates the length, the others are measurements
+    GSN_CUDA(cudaEventRecord(e0));
+    dmma_peak_kernel<<<blocks, threads>>>(out.as<double>(), iters);
+    GSN_CUDA(cudaEventRecord(e1));
+    GSN_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    GSN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 512.0 * 8.0 * iters * (double)(blocks * (threads / 32)) / (ms * 1e-3) / 1e12;
+    if (rep > 0) best = std::max(best, tf);
+    if (rep == 0 && ms > 0.f) iters = std::max(1000, (int)(iters * (seconds * 1e3 / 3.0) / ms));
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops_out = best;
+  return GSN_OK;
+}
+
 int64_t gsn_query(const gsn_problem* p, int32_t what) {
   if (!p) return -1;
   switch (what) {
@@ -916,13 +976,6 @@ int64_t gsn_query(const gsn_problem* p, int32_t what) {
 // ---------------------------------------------------------------------------
 // single-call plugin evaluations (host pointers)
 // ---------------------------------------------------------------------------
-static int open_device(int device) {
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    return fail(GSN_ERR_CUDA, "no CUDA device available; libgsn has no CPU path");
-  if (device < 0 || device >= ndev) return fail(GSN_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
-  return GSN_OK;
-}
 
 int gsn_covariance(int device, int32_t kernel_kind, const double* params, int32_t n_params, const double* x, int64_t n,
                    const double* x_prime, int64_t m, double* K_out) {

@@ -57,6 +57,9 @@ static __constant__ double kExpC[8] = {
 // kernel constants and the shifted epochs once per theta).  Results that would be
 // subnormal (x < -708.4) are flushed to zero, overflow gives +inf.
 __device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab) {
+#ifdef GSN_ACCURATE_EXP   // accuracy experiments (tools/arbiter_check.py): libdevice's exp, < 1 ulp
+  return exp(x);
+#endif
   const double t = fma(x, kExpC[0], kExpC[1]);
   const int n = __double2loint(t);
   const double nf = t - kExpC[1];

@@ -56,6 +56,8 @@ class GP:
             if not hasattr(plugin, "kind"):
                 raise TypeError(f"{type(plugin).__name__} is not a gaussn_b200 {what}: only plugins with a device "
                                 "implementation can be used (there is no CPU fallback)")
+            if device is not None and getattr(plugin, "device", None) is None:
+                plugin.device = device      # the plugins' own covariance / mean / lens calls run on the GP's GPU
 
     # ------------------------------------------------------------------ bookkeeping
     def _prepare_indices(self, x, band, image):

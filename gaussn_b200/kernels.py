@@ -34,7 +34,7 @@ class _Kernel:
     def covariance(self, x, x_prime=None, params=None):
         if params is not None:
             self._reset(params)
-        return _engine.covariance(self.kind, [float(v) for v in self.params[:len(self._names)]], x, x_prime)
+        return _engine.covariance(self.kind, [float(v) for v in self.params[:len(self._names)]], x, x_prime, device=getattr(self, "device", None))
 
     _covariance = covariance   # the reference exposes both names (kernels.py:20, :30)
 
@@ -70,7 +70,7 @@ class DotProductKernel(_Kernel):
         self.c = 0
 
     def covariance(self, x, x_prime=None, params=None):
-        return _engine.covariance(self.kind, [], x, x_prime)
+        return _engine.covariance(self.kind, [], x, x_prime, device=getattr(self, "device", None))
 
     _covariance = covariance
 

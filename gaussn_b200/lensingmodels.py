@@ -78,7 +78,7 @@ class _Magnification:
         if len(self.params) != self.per_image * (self.n_images - 1):
             raise IndexError(f"{type(self).__name__}: {self.n_images} images need "
                              f"{self.per_image * (self.n_images - 1)} parameters, got {len(self.params)}")
-        return _engine.lens(self.kind, [float(v) for v in self.params], x, self.n_bands, self.n_images, self.indices)
+        return _engine.lens(self.kind, [float(v) for v in self.params], x, self.n_bands, self.n_images, self.indices, device=getattr(self, "device", None))
 
     _lens = lens
 

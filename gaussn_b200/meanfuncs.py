@@ -35,7 +35,7 @@ class _Mean:
     def mean(self, y, params=None, bands=None, zp=None, zpsys=None):
         if params is not None:
             self._reset(params)
-        return _engine.mean(self.kind, [float(v) for v in self.params[:len(self._names)]], y)
+        return _engine.mean(self.kind, [float(v) for v in self.params[:len(self._names)]], y, device=getattr(self, "device", None))
 
 
 class UniformMean(_Mean):

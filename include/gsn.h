@@ -213,6 +213,10 @@ int gsn_predict_batch_host(gsn_problem* p, const double* theta_host, int64_t B, 
 
 int64_t gsn_query(const gsn_problem* p, int32_t what);
 
+/* Measurement aid, not part of the reference's surface: the FP64 tensor-pipe rate of `device` in TFLOP/s (back-to-back
+ * independent DMMA.8x8x4 chains on every SM for about `seconds`), i.e. the roofline denominator bench.py reports against. */
+int gsn_measure_fp64_peak(int device, double seconds, double* tflops_out);
+
 /* Introspection, no device needed: the order in which the work items (32x32 blocks (c, j), c >= j, of the blocked
  * Cholesky) of one evaluation are handed to warps, as built by gsn_problem_create for a data set of N rows whose
  * band index per row is band_of_row (NULL = one band).  Item word: (first_col << 24) | (c << 12) | j.  Returns the
@@ -250,6 +254,7 @@ int32_t gsn_mean_nparams(int32_t mean_kind);
 int32_t gsn_lens_nparams(int32_t lens_kind, int32_t n_images);
 
 int32_t gsn_abi_version(void);
+int32_t gsn_device_count(void);   /* CUDA devices visible to this process (0 without a driver) */
 const char* gsn_last_error(void);
 
 #ifdef __cplusplus

@@ -8,7 +8,11 @@ m = dict(zip(hdr, vals))
 keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'launch__registers_per_thread', 'launch__grid_size',
         'sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
-        'sm__warps_active.avg.pct_of_peak_sustained_active', 'lts__t_bytes.sum', 'lts__t_bytes.sum.per_second']
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'lts__t_bytes.sum', 'lts__t_bytes.sum.per_second',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'launch__shared_mem_per_block_dynamic', 'launch__occupancy_limit_shared_mem',
+        'launch__occupancy_limit_registers', 'launch__block_size', 'sm__cycles_elapsed.avg', 'sm__inst_executed_pipe_fp64.sum', 'smsp__inst_executed_pipe_lsu.sum']
 for k in keys:
     if k in m: print(f'{k:85s} {m[k]:>18s} {units[hdr.index(k)]}')
 print('stall mix (warps per issue-active):')

@@ -6,7 +6,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import benchdata
 from gaussn_b200 import gausSN, kernels, meanfuncs, lensingmodels
 
+ONLY = sys.argv[1:]          # optional substrings: run only the configurations whose name contains one of them
+
+
 def run(name, N, n_bands, n_images, kernel, kp, mean, mp, lens, lp_per, B, kname):
+    if ONLY and not any(o in name for o in ONLY):
+        return
     ds = benchdata.make_dataset(N, n_bands, n_images, span=150.0 if N < 1000 else 2.0 * N / n_images)
     rng = np.random.default_rng(3)
     cols = [rng.uniform(lo, hi, B) for lo, hi in kp + mp]
@@ -29,7 +34,8 @@ def run(name, N, n_bands, n_images, kernel, kp, mean, mp, lens, lp_per, B, kname
     flops = benchdata.algorithmic_flops(N, n_bands, lens is not None, kname)
     print(json.dumps(dict(config=name, N=N, bands=n_bands, images=n_images, P=theta.shape[1], B=B, ms=ms, evals_per_s=B / ms * 1e3,
                           tflops=flops * B / ms / 1e9, frac_of_fp64_peak=flops * B / ms / 1e9 / 37.165,
-                          finite=float(torch.isfinite(out).float().mean()))), flush=True)
+                          finite=float(torch.isfinite(out).float().mean()), shape=int(gp._problem.query(10)),
+                          warps_per_theta=int(gp._problem.query(15)))), flush=True)
 
 A, TAU, C = (0.05, 1.0), (10, 40), (-0.2, 0.2)
 CM = [(0, 60), (0.1, 1.0)]
