@@ -89,6 +89,10 @@ struct gsn_problem {
   double* d_theta = nullptr; double* d_logl = nullptr; int* d_info = nullptr;
   int64_t stage_rows = 0; int64_t stage_ld = 0;
   cudaStream_t own_stream = nullptr;
+  // Stream contract: a handle owns ONE counter, workspace, theta map and prediction workspace, but callers may launch on any
+  // stream (and the host-buffer entry points use own_stream).  Every launch is ordered behind the handle's previous launch
+  // through this event, whatever streams the two were issued on; host-side updates of the handle wait for it.
+  cudaEvent_t last_launch = nullptr;
   long long launches = 0;
   // gsn_predict_batch: workspace and item list, sized on demand
   double* d_pred_ws = nullptr; size_t pred_ws_bytes = 0;
@@ -113,8 +117,36 @@ int ensure_workspace(gsn_problem* p, int64_t slots) {
   return GSN_OK;
 }
 
+// Order `stream` behind the handle's previous launch (no-op on the same stream, an event wait otherwise).
+int order_after_last_launch(gsn_problem* p, cudaStream_t stream) {
+  GSN_CUDA(cudaStreamWaitEvent(stream, p->last_launch, 0));
+  return GSN_OK;
+}
+int mark_launch(gsn_problem* p, cudaStream_t stream) {
+  GSN_CUDA(cudaEventRecord(p->last_launch, stream));
+  p->launches += 1;
+  return GSN_OK;
+}
+// Before the host rewrites device state of the handle (observations, theta map, item lists, workspaces).
+int wait_for_last_launch(gsn_problem* p) {
+  GSN_CUDA(cudaEventSynchronize(p->last_launch));
+  return GSN_OK;
+}
+
+int dispatch_logl_out_impl(gsn_problem* p, const double* theta, int64_t B, int64_t ld, const double* hostmean,
+                           const gsn::GatherOut& out, int* info, unsigned flags, cudaStream_t stream);
+
 int dispatch_logl_out(gsn_problem* p, const double* theta, int64_t B, int64_t ld, const double* hostmean,
                       const gsn::GatherOut& out, int* info, unsigned flags, cudaStream_t stream) {
+  if (int rc = order_after_last_launch(p, stream)) return rc;
+  const long long before = p->launches;
+  if (int rc = dispatch_logl_out_impl(p, theta, B, ld, hostmean, out, info, flags, stream)) return rc;
+  p->launches = before;
+  return mark_launch(p, stream);
+}
+
+int dispatch_logl_out_impl(gsn_problem* p, const double* theta, int64_t B, int64_t ld, const double* hostmean,
+                           const gsn::GatherOut& out, int* info, unsigned flags, cudaStream_t stream) {
   GSN_CUDA(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned), stream));
   // One warp per theta pays off once there are enough thetas to fill the GPU with such CTAs; for small batches
   // (and single calls, which is how the reference's samplers use the likelihood) four warps per theta give the
@@ -608,6 +640,7 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
     }
   }
   GSN_CUDA_P(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+  GSN_CUDA_P(cudaEventCreateWithFlags(&p->last_launch, cudaEventDisableTiming));
 #undef GSN_CUDA_P
   *out = p;
   return GSN_OK;
@@ -625,6 +658,7 @@ int gsn_problem_destroy(gsn_problem* p) {
   if (p->h_logl) cudaFreeHost(p->h_logl);
   if (p->h_info) cudaFreeHost(p->h_info);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
+  if (p->last_launch) cudaEventDestroy(p->last_launch);
   delete p;
   return GSN_OK;
 }
@@ -640,6 +674,7 @@ int gsn_problem_set_data(gsn_problem* p, const double* x, const double* y, const
   }
   (void)N;
   DeviceGuard guard(p->device);
+  if (int rc = wait_for_last_launch(p)) return rc;     // the observations may still be read by a launch in flight
   const size_t nb = sizeof(double) * Npad;
   GSN_CUDA(cudaMemcpy(p->d_x, hx.data(), nb, cudaMemcpyHostToDevice));
   GSN_CUDA(cudaMemcpy(p->d_y, hy.data(), nb, cudaMemcpyHostToDevice));
@@ -673,6 +708,7 @@ int gsn_problem_set_theta_map(gsn_problem* p, const int32_t* col_of_param, const
     ncols = std::max(ncols, c + 1);
   }
   DeviceGuard guard(p->device);
+  if (int rc = wait_for_last_launch(p)) return rc;     // the map may still be read by a launch in flight
   GSN_CUDA(cudaMemcpy(p->d_theta_col, hcol.data(), sizeof(int) * hcol.size(), cudaMemcpyHostToDevice));
   GSN_CUDA(cudaMemcpy(p->d_theta_fixed, hfix.data(), sizeof(double) * hfix.size(), cudaMemcpyHostToDevice));
   p->n_theta_cols = ncols;
@@ -730,10 +766,10 @@ int gsn_lens_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_t l
   if (B > 0 && !b_dev) return fail(GSN_ERR_INVALID, "b_dev is null");
   if (B == 0) return GSN_OK;
   DeviceGuard guard(p->device);
+  if (int rc = order_after_last_launch(p, (cudaStream_t)cuda_stream)) return rc;   // the theta map may be in use
   gsn::lens_batch_kernel<<<(unsigned)B, 128, 0, (cudaStream_t)cuda_stream>>>(p->pd, theta_dev, B, ld, shifted_dev, b_dev);
   GSN_CUDA(cudaGetLastError());
-  p->launches += 1;
-  return GSN_OK;
+  return mark_launch(p, (cudaStream_t)cuda_stream);
 }
 
 int gsn_logl_batch_host(gsn_problem* p, const double* theta_host, int64_t B, int64_t ld, double* logl_host,
@@ -848,13 +884,13 @@ int gsn_predict_batch(gsn_problem* p, const double* theta_dev, int64_t B, int64_
     GSN_CUDA(cudaMalloc(&p->d_pred_ws, (size_t)grid * slot_bytes));
     p->pred_ws_bytes = (size_t)grid * slot_bytes;
   }
+  if (int rc = order_after_last_launch(p, stream)) return rc;
   GSN_CUDA(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned), stream));
   gsn::PredictLaunchArgs a{p->pd, pa, theta_dev, B, ld, info_dev, p->d_pred_ws, p->d_counter, cl ? (grid << cl) : grid, smem, stream,
                            1 << cl};
   const cudaError_t e = (k <= 4) ? gsn::launch_predict_a(k, &a) : gsn::launch_predict_b(k, &a);
   if (e != cudaSuccess) return fail(GSN_ERR_CUDA, "prediction kernel launch failed: %s", cudaGetErrorString(e));
-  p->launches += 1;
-  return GSN_OK;
+  return mark_launch(p, stream);
 }
 
 int gsn_predict_batch_host(gsn_problem* p, const double* theta_host, int64_t B, int64_t ld, int64_t row0, int64_t n_rows,

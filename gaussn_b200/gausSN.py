@@ -358,8 +358,11 @@ class GP:
             nlive = sampler_kwargs.pop('nlive', 500)
             sample = sampler_kwargs.pop('sample', 'rslice')
             if isinstance(sampler_kwargs.get('pool'), samplers.BatchPool):
-                # batched queue evaluation: the pool recognises this callable and evaluates whole queues at once
+                # Batched evaluation.  The initial live points are one launch (the pool finds this callable inside dynesty's
+                # wrappers); the proposals -- `queue_size` walks of evolve_point per pool.map, each calling the likelihood
+                # one point at a time -- run in lock step on threads and meet at a rendezvous, one launch per round.
                 post = samplers.VectorizedPosterior(self, *args)
+                sampler_kwargs['pool'].posterior = post
                 sampler_kwargs.setdefault('queue_size', sampler_kwargs['pool'].size)
                 sampler = dynesty.NestedSampler(post, ptform, self.ndim, nlive=nlive, sample=sample, **sampler_kwargs)
                 sampler.run_nested(**run_sampler_kwargs)
@@ -452,12 +455,13 @@ class GP:
         return e[0], v[0]
 
     def predict_batch(self, theta, x_prime, band=None, fix_kernel_params=False, fix_mean_params=False,
-                      fix_lensing_params=False, return_cov=True):
+                      fix_lensing_params=False, return_cov=True, band_index=None):
         """``predict`` for every row of ``theta`` (e.g. equal-weight posterior samples) on the data set given to
         ``optimize_parameters``, the way the reference's plotting loop uses it (gaussn/utils.py:156-209): per sample,
         the observations of ``band`` are shifted by the sample's time delays and divided by its magnifications, and the
-        GP is conditioned on them at ``x_prime`` (epochs in the frame of the first image).  ``band`` is a band label,
-        its index in ``np.unique`` order, or ``None`` for all rows.  Returns ``expectation [B, M]`` and
+        GP is conditioned on them at ``x_prime`` (epochs in the frame of the first image).  ``band`` is a band LABEL (an entry
+        of the ``band`` array given to ``optimize_parameters`` -- also when the labels are integers), ``band_index`` its
+        position in ``np.unique`` order; neither: all rows.  Returns ``expectation [B, M]`` and
         ``variance [B, M, M]`` (``None`` with ``return_cov=False``) -- numpy for a numpy ``theta``, CUDA tensors for a
         CUDA ``theta``.  The whole batch is one kernel launch."""
         self._ensure_problem(self.x, self.y, self.yerr)
@@ -465,11 +469,20 @@ class GP:
             fix_lensing_params = True
         ncols = self._set_map(fix_kernel_params, fix_mean_params, fix_lensing_params)
         p = self._problem
-        if band is None:
+        if band is None and band_index is None:
             row0, row1, label = 0, p.N, None
         else:
             labels = list(np.unique(self.bands)) if self.bands is not None else [None]
-            b = band if isinstance(band, (int, np.integer)) else labels.index(band)
+            if band is not None and band_index is not None:
+                raise ValueError("give band (a label) or band_index (a position), not both")
+            if band is not None:
+                if band not in labels:
+                    raise ValueError(f"band {band!r} is not one of the labels {labels}; use band_index= to select by position")
+                b = labels.index(band)
+            else:
+                b = int(band_index)
+                if not 0 <= b < len(labels):
+                    raise IndexError(f"band_index {b} out of range for {len(labels)} bands")
             label = labels[b]
             row0, row1 = int(self.indices[b * self.n_images]), int(self.indices[(b + 1) * self.n_images])
         x_prime = np.ascontiguousarray(np.asarray(x_prime, dtype=np.float64)).ravel()

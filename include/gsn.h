@@ -19,7 +19,14 @@
  *     with GSN_FLAG_NEG_INF, which is what GP.jointprobability returns,
  *     gaussn/gausSN.py:203-204) and info[i] != 0;
  *   - there is no CPU fallback: without a CUDA device every compute entry point
- *     fails with GSN_ERR_CUDA.
+ *     fails with GSN_ERR_CUDA;
+ *   - streams: a handle owns one set of scratch state (work counter, factor
+ *     workspace, theta map), so its launches are serialised on the device: every
+ *     batch call is ordered behind the handle's previous launch by an event,
+ *     whichever streams the two were issued on (the *_host entry points use a
+ *     stream of the handle's own).  gsn_problem_set_data / _set_theta_map wait for
+ *     the last launch before they touch device state.  Calls on ONE handle must
+ *     not be made from two host threads at once; different handles are independent.
  */
 #ifndef GSN_H_
 #define GSN_H_
@@ -137,7 +144,7 @@ int gsn_problem_destroy(gsn_problem* p);
 /* Replace the observations of a handle in place (same N, same band / image structure): what the reference does
  * when its plotting loop builds a fresh GP for every posterior sample and band (gaussn/utils.py:193-204) or when
  * optimize_parameters is called again with new data (gausSN.py:276-280) -- without paying for a new handle.
- * No batch call on this handle may be in flight. */
+ * Waits for the handle's launches in flight. */
 int gsn_problem_set_data(gsn_problem* p, const double* x, const double* y, const double* yerr);
 
 /*

@@ -29,7 +29,7 @@ def _oracle_predict_band(ds, gp, theta_row, kernel, mean, lens, x_prime, band_in
 
 
 def _check(gp, ds, theta, kernel, mean, lens, x_prime, band_index, what):
-    e, v = gp.predict_batch(theta, x_prime, band=band_index)
+    e, v = gp.predict_batch(theta, x_prime, band_index=band_index)
     assert e.shape == (len(theta), len(x_prime)) and v.shape == (len(theta), len(x_prime), len(x_prime))
     for i, row in enumerate(theta):
         e0, v0 = _oracle_predict_band(ds, gp, row, kernel, mean, lens, x_prime, band_index)
@@ -88,10 +88,10 @@ def test_predict_band_by_label_and_expectation_only(libgsn):
     theta = _theta_box(rng, 8, "OUKernel", "UniformMean", "ConstantMagnification", 2)
     gp = _prepared(ds, "OUKernel", "UniformMean", "ConstantMagnification", 2, theta[0])
     x_prime = np.linspace(0, 120, 45)
-    e_idx, v_idx = gp.predict_batch(theta, x_prime, band=1)
+    e_idx, v_idx = gp.predict_batch(theta, x_prime, band_index=1)
     e_lab, v_lab = gp.predict_batch(theta, x_prime, band="b1")
     assert np.array_equal(e_idx, e_lab) and np.array_equal(v_idx, v_lab)
-    e_only, none = gp.predict_batch(theta, x_prime, band=1, return_cov=False)
+    e_only, none = gp.predict_batch(theta, x_prime, band_index=1, return_cov=False)
     assert none is None and np.array_equal(e_only, e_idx)
 
 
@@ -102,7 +102,7 @@ def test_predict_fixed_groups(libgsn):
     theta = _theta_box(rng, 6, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", 2)
     x_prime = np.linspace(0, 120, 33)
     gp = _prepared(ds, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", 2, theta[0])
-    e, v = gp.predict_batch(theta[:, 2:], x_prime, band=0, fix_kernel_params=True)
+    e, v = gp.predict_batch(theta[:, 2:], x_prime, band_index=0, fix_kernel_params=True)
     for i, row in enumerate(theta):
         full = np.concatenate([theta[0, :2], row[2:]])
         e0, v0 = _oracle_predict_band(ds, gp, full, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", x_prime, 0)
@@ -117,8 +117,8 @@ def test_predict_device_tensors_match_host_buffers_bitwise(libgsn):
     theta = _theta_box(rng, 40, "Matern52Kernel", "UniformMean", "ConstantMagnification", 2)
     gp = _prepared(ds, "Matern52Kernel", "UniformMean", "ConstantMagnification", 2, theta[0])
     x_prime = np.linspace(0, 130, 77)
-    e_h, v_h = gp.predict_batch(theta, x_prime, band=0)
-    e_d, v_d = gp.predict_batch(torch.as_tensor(theta, device="cuda"), x_prime, band=0)
+    e_h, v_h = gp.predict_batch(theta, x_prime, band_index=0)
+    e_d, v_d = gp.predict_batch(torch.as_tensor(theta, device="cuda"), x_prime, band_index=0)
     assert e_d.is_cuda and v_d.is_cuda
     assert np.array_equal(e_d.cpu().numpy(), e_h) and np.array_equal(v_d.cpu().numpy(), v_h)
 
@@ -131,12 +131,12 @@ def test_predict_pieces_of_a_long_grid_agree_with_one_call(libgsn, monkeypatch):
     theta = _theta_box(rng, 4, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", 2)
     gp = _prepared(ds, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", 2, theta[0])
     x_prime = np.linspace(0, 130, 100)
-    e1, v1 = gp.predict_batch(theta, x_prime, band=0)
+    e1, v1 = gp.predict_batch(theta, x_prime, band_index=0)
     monkeypatch.setattr(_engine, "MAX_ORDER", 64 + 70)     # room for 70 epochs: pieces of 35
-    e2, v2 = gp.predict_batch(theta, x_prime, band=0)
+    e2, v2 = gp.predict_batch(theta, x_prime, band_index=0)
     np.testing.assert_allclose(e2, e1, rtol=1e-12, atol=1e-13)
     np.testing.assert_allclose(v2, v1, rtol=1e-10, atol=1e-13)
-    e3, _ = gp.predict_batch(theta, x_prime, band=0, return_cov=False)
+    e3, _ = gp.predict_batch(theta, x_prime, band_index=0, return_cov=False)
     np.testing.assert_allclose(e3, e1, rtol=1e-12, atol=1e-13)
 
 
@@ -178,7 +178,7 @@ def test_predict_with_host_supplied_mean(libgsn):
     gp.x, gp.y, gp.yerr, gp.bands = ds["x"], ds["y"], ds["yerr"], ds["band"]
     gp._prepare_indices(ds["x"], ds["band"], ds["image"])
     x_prime = np.linspace(0, 120, 21)
-    e, v = gp.predict_batch(theta, x_prime, band=1)
+    e, v = gp.predict_batch(theta, x_prime, band_index=1)
     for i, row in enumerate(theta):
         e0, v0 = _oracle_predict_band(ds, gp, row, "ExpSquaredKernel", "Bazin2009", "ConstantMagnification", x_prime, 1)
         np.testing.assert_allclose(e[i], e0, **E_TOL)
@@ -272,6 +272,26 @@ def test_predict_batch_against_reference_plotting_loop_vectors(libgsn):
         gp = make_gp(ds, case["kernel"], th[:nk], case["mean"], th[nk:nk + nm], case["lensing"], th[nk + nm:])
         gp.bands = np.array(ds["band"])
         for bi, want in enumerate(case["bands"]):
-            e, v = gp.predict_batch(th[None, :], np.array(case["x_prime"]), band=bi)
+            e, v = gp.predict_batch(th[None, :], np.array(case["x_prime"]), band_index=bi)
             np.testing.assert_allclose(e[0], want["expectation"], **E_TOL)
             np.testing.assert_allclose(v[0].ravel(), want["variance"], **V_TOL)
+
+
+def test_integer_band_labels_are_labels_not_positions(libgsn):
+    """Filter ids 1, 2 as band labels: band=2 is the SECOND band (a label), band_index=1 the same by position; a value that
+    is not a label raises instead of silently selecting another band's rows."""
+    rng = np.random.default_rng(73)
+    ds = _synth(rng, 90, 2, 2)
+    ds = dict(ds, band=np.where(ds["band"] == "b0", 1, 2))
+    theta = _theta_box(rng, 4, "OUKernel", "UniformMean", "ConstantMagnification", 2)
+    gp = _prepared(ds, "OUKernel", "UniformMean", "ConstantMagnification", 2, theta[0])
+    x_prime = np.linspace(0, 120, 20)
+    e2, v2 = gp.predict_batch(theta, x_prime, band=2)
+    e_pos, v_pos = gp.predict_batch(theta, x_prime, band_index=1)
+    assert np.array_equal(e2, e_pos) and np.array_equal(v2, v_pos)
+    e1, _ = gp.predict_batch(theta, x_prime, band=1)
+    assert not np.array_equal(e1, e2)
+    with pytest.raises(ValueError, match="not one of the labels"):
+        gp.predict_batch(theta, x_prime, band=0)
+    with pytest.raises(ValueError, match="not both"):
+        gp.predict_batch(theta, x_prime, band=1, band_index=0)

@@ -52,13 +52,13 @@ def main():
                                 [rng.uniform(8, 12, B) if k % 2 == 0 else rng.uniform(0.8, 1.0, B) for k in range(2 * (n_images - 1))])
         th_d = torch.as_tensor(theta, device="cuda")
         x_prime = np.linspace(0, 160, M)
-        gp.predict_batch(th_d, x_prime, band=0)            # warm-up: kernel image, workspace, item list
+        gp.predict_batch(th_d, x_prime, band_index=0)            # warm-up: kernel image, workspace, item list
         torch.cuda.synchronize()
         reps = 5
         t0 = time.perf_counter()
         for _ in range(reps):
             for b in range(n_bands):
-                e, v = gp.predict_batch(th_d, x_prime, band=b)
+                e, v = gp.predict_batch(th_d, x_prime, band_index=b)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / reps
         n_rows = int(gp.indices[n_images] - gp.indices[0])
