@@ -438,6 +438,13 @@ logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta
         for (int n = tid; n < nt * (nt + 1) / 2; n += nthreads) tab[n] = src[n];
         for (int n = tid; n < nt; n += nthreads) ctl->cdone[n] = 0;
       }
+#ifdef GSN_ONCHIP_POISON
+      // Debug build (compute-sanitizer is closed on this pool): every tile slot starts as NaN, so a tile that is read before
+      // it was written in THIS block -- a wrong slot table, a missing wait -- turns the result into NaN and fails the parity
+      // tests.  Rows whose slots are recycled are poisoned again by whoever recycles them (see may_write).
+      for (int n = tid; n < od.n_slots * 32; n += nthreads)
+        reinterpret_cast<double2*>(sm + lay.off_tiles)[n] = make_double2(__longlong_as_double(0x7ff8dead00000000LL), __longlong_as_double(0x7ff8dead00000000LL));
+#endif
       if (tid == 0) { ctl->prog_row = 1; ctl->prog_diag = 0; ctl->prog_z = 0; }
       if (__syncthreads_or(bad)) { dead = true; break; }
       bad = 0;

@@ -172,3 +172,21 @@ def test_new_observations_reach_the_on_chip_tables(libgsn):
     got = gp.loglikelihood_batch(theta, x=ds2["x"], y=ds2["y"], yerr=ds2["yerr"])
     assert gp._problem is handle
     assert_logl_close(got, _oracle_batch(ds2, theta, "Matern32Kernel", "UniformMean", "ConstantMagnification", gp), "set_data")
+
+
+@pytest.mark.parametrize("n_bands,n_images,N,kernel", [(1, 3, 141, "OUKernel"), (4, 2, 194, "ExpSquaredKernel"), (1, 2, 190, "Matern32Kernel")])
+def test_repeated_runs_with_every_team_size_are_bit_identical(libgsn, monkeypatch, n_bands, n_images, N, kernel):
+    """Race detector of our own (compute-sanitizer is closed on this pool): the dataflow between the warps of a team --
+    progress counters, column counters that guard the recycling of tile slots -- is exercised 25 times per team size with
+    several waves of thetas per SM; a missing wait shows up as a value that depends on timing."""
+    rng = np.random.default_rng(N + n_bands)
+    ds = _synth(rng, N, n_bands, n_images)
+    theta = _theta_box(rng, 1500, kernel, "UniformMean", "ConstantMagnification", n_images)
+    gp = _gp_for(ds, kernel, "UniformMean", "ConstantMagnification", n_images, theta[0])
+    ref = gp.loglikelihood_batch(theta)
+    assert np.isfinite(ref).sum() > 1400
+    for T in (2, 4, 8, 16):
+        monkeypatch.setenv("GSN_ONCHIP_T", str(T))
+        for rep in range(25):
+            got = gp.loglikelihood_batch(theta)
+            assert np.array_equal(got, ref, equal_nan=True), f"T={T} repetition {rep}: {int(np.sum(got != ref))} values differ"
