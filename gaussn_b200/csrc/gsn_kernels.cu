@@ -45,4 +45,15 @@ static cudaError_t dispatch(int kind, const LaunchArgs* a) {   // a == nullptr: 
 
 cudaError_t GSN_SLICE_NAME(int kind, const LaunchArgs* a) { return dispatch<GSN_SLICE_LO>(kind, a); }
 
+#if defined(GSN_PHASE_TIMERS) && defined(GSN_PHASE_EXPORT)
+extern "C" int gsn_debug_phase_cycles(unsigned long long* out, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 16);
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[16] = {0};
+    e = cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z);
+  }
+  return (int)e;
+}
+#endif
+
 }  // namespace gsn

@@ -230,7 +230,33 @@ class GP:
             self.lensingmodel._reset(list(lensing_params))
         self._ensure_problem(x, y, yerr)
         self._set_map(True, True, True)
+        self._last_call = (np.asarray(x, dtype=np.float64), np.asarray(yerr, dtype=np.float64))   # for the lazy .mean / .cov
+        self._mean_cache = self._cov_cache = None
         return float(self._evaluate(np.zeros((1, 0)))[0])
+
+    # The reference leaves ``self.mean`` and ``self.cov`` of the last ``loglikelihood`` call behind (gausSN.py:142, :147).  The
+    # engine never materialises either, so they are produced on demand, from the plugins' current parameters and the data of
+    # that call, through the plugins' own device evaluations.
+    @property
+    def mean(self):
+        if getattr(self, "_last_call", None) is None:
+            raise AttributeError("mean is available after a loglikelihood call")
+        if self._mean_cache is None:
+            x, _ = self._last_call
+            shifted, b = self.lensingmodel.lens(x)
+            self._mean_cache = b * np.asarray(self.meanfunc.mean(shifted, bands=self.bands, zp=self.zp, zpsys=self.zpsys))
+        return self._mean_cache
+
+    @property
+    def cov(self):
+        if getattr(self, "_last_call", None) is None:
+            raise AttributeError("cov is available after a loglikelihood call")
+        if self._cov_cache is None:
+            x, yerr = self._last_call
+            shifted, b = self.lensingmodel.lens(x)
+            K = np.outer(b, b) * np.asarray(self.kernel.covariance(shifted))
+            self._cov_cache = np.multiply(self.lensingmodel.mask, K) + np.diag(yerr ** 2)
+        return self._cov_cache
 
     def loglikelihood_batch(self, theta, x=None, y=None, yerr=None, fix_kernel_params=False, fix_mean_params=False,
                             fix_lensing_params=False, neg_inf=False):

@@ -585,3 +585,23 @@ def test_minimize_finds_the_reference_optimum(libgsn, golden):
         # not the same iterates
         assert abs(res.fun - case["fun"]) <= 1e-8, (res.fun, case["fun"])
         np.testing.assert_allclose(res.x, case["x"], rtol=1e-5, atol=1e-5)
+
+
+def test_mean_and_cov_of_the_last_loglikelihood_call(libgsn):
+    """The reference leaves self.mean and self.cov behind (gausSN.py:142, :147); here they are produced on demand."""
+    rng = np.random.default_rng(31)
+    ds = _synth(rng, 60, 2, 2)
+    kp, mp, lp = [0.3, 9.0], [0.8, 0.05, 30.0, 40.0, 8.0], [7.0, 0.8]
+    gp = make_gp(ds, "Matern32Kernel", kp, "Bazin2009", mp, "ConstantMagnification", lp)
+    with pytest.raises(AttributeError):
+        gp.mean
+    ll = gp.loglikelihood(ds["x"], ds["y"], ds["yerr"], kp, mp, lp)
+    want_mean, want_cov = gp_oracle.build_mean_cov(ds["x"], ds["yerr"], "Matern32Kernel", kp, "Bazin2009", mp, "ConstantMagnification", lp,
+                                                   gp.n_bands, gp.n_images, gp.indices)
+    np.testing.assert_allclose(gp.mean, want_mean, rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(gp.cov, want_cov, rtol=1e-13, atol=1e-300)
+    # and they are what the likelihood was computed from
+    import scipy.linalg
+    L = np.linalg.cholesky(gp.cov)
+    z = scipy.linalg.solve_triangular(L, gp.mean - ds["y"], lower=True)
+    assert abs(-0.5 * (len(z) * np.log(2 * np.pi) + 2 * np.sum(np.log(np.diag(L))) + z @ z) - ll) <= 1e-8
