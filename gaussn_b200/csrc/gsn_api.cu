@@ -148,23 +148,24 @@ int dispatch_logl_out(gsn_problem* p, const double* theta, int64_t B, int64_t ld
 int dispatch_logl_out_impl(gsn_problem* p, const double* theta, int64_t B, int64_t ld, const double* hostmean,
                            const gsn::GatherOut& out, int* info, unsigned flags, cudaStream_t stream) {
   GSN_CUDA(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned), stream));
-  // One warp per theta pays off once there are enough thetas to fill the GPU with such CTAs; for small batches
-  // (and single calls, which is how the reference's samplers use the likelihood) four warps per theta give the
-  // lower latency (N = 141: 96 us against 161 us per call; B = 4096: 1.04 ms against 1.33 ms the other way round).
   const int k = p->kernel_kind;
   if (p->onchip_ok) {
     // Small band blocks: the factor never leaves the SM.  T warps share one theta; T is the smallest team that fills an SM
     // with warps given how many thetas its shared memory holds, and larger for calls with too few thetas to fill the GPU.
     // Results do not depend on T (same tile arithmetic, whoever runs it).
     const int warps_max = std::max(1, std::min(64, 65536 / (((p->onchip_regs + 7) / 8 * 8) * 32)));
-    // (more thetas in flight beat larger teams: N = 160 runs 7.6 M evals/s as 3 x 4 warps per SM against 7.1 M as 2 x 8)
-    int target = 12;
+    // Team size: enough warps per SM to hide latency (about 15), given how many thetas the shared memory holds -- more thetas
+    // in flight beat larger teams (N = 160: 7.7 M evals/s as 3 thetas x 5 warps, 7.1 M as 2 x 8; N = 141: 11.0 M as 3 x 5,
+    // 10.5 M as 3 x 4, 9.6 M as 3 x 6) -- and never more warps than half the tile rows; a team may have any size up to 16.
+    int target = 15;
     if (const char* e = getenv("GSN_ONCHIP_WARPS_PER_SM")) target = std::max(1, atoi(e));
-    int t_cap = 1;
-    while (t_cap < gsn::kOnchipMaxWarps && 2 * t_cap <= p->od.nt_max) t_cap *= 2;   // a team larger than the tile rows idles
-    int T = 1;
-    while (T < t_cap && T * p->onchip_ctas_smem < target) T *= 2;
-    while (T < t_cap && B * T * 2 <= (int64_t)p->sm_count * 4) T *= 2;               // few thetas: shorter critical path per theta
+    const int t_cap = std::max(1, std::min(gsn::kOnchipMaxWarps, p->od.nt_max / 2));
+    int T = (target + p->onchip_ctas_smem - 1) / p->onchip_ctas_smem;
+    if (p->onchip_ctas_smem >= 10) T = 1;     // ten and more one-warp thetas per SM: N = 64 runs 55 M evals/s so, 52 M as teams of two
+    if (T > 8) T = gsn::kOnchipMaxWarps;
+    T = std::max(1, std::min(T, t_cap));
+    // few thetas: larger teams shorten the critical path of each
+    while (T < t_cap && B * T * 2 <= (int64_t)p->sm_count * 4) T = std::min(t_cap, T * 2);
     if (const char* e = getenv("GSN_ONCHIP_T")) T = std::max(1, std::min(gsn::kOnchipMaxWarps, atoi(e)));
     const size_t smem = p->smem_onchip;
     const int ctas_smem = p->onchip_ctas_smem;
@@ -196,6 +197,9 @@ int dispatch_logl_out_impl(gsn_problem* p, const double* theta, int64_t B, int64
     p->launches += 1;
     return GSN_OK;
   }
+  // Workspace kernels.  One warp per theta pays off once there are enough thetas to fill the GPU with such CTAs; for small
+  // batches (and single calls, which is how the reference's samplers use the likelihood) four warps per theta give the
+  // lower latency.
   int64_t narrow_min = p->narrow_min_batch;
   if (const char* nm_env = getenv("GSN_NARROW_MIN_BATCH")) narrow_min = atoll(nm_env);   // tuning hook
   const bool narrow = p->narrow_ok && B >= narrow_min;

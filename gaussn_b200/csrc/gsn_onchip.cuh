@@ -328,7 +328,7 @@ struct OnchipTeam {
   __device__ __forceinline__ void factor(int warp) const {
     for (int j = -1; j < nt - 1; ++j) {
       if (ld_volatile_shared(&ctl->fail) != 0) break;
-      int i = (j + 1) + ((warp - (j + 1)) & (T - 1));   // this warp's first row below j
+      int i = (j + 1) + (warp - (j + 1) % T + T) % T;   // this warp's first row below j (rows are dealt out cyclically)
       bool ok = true, write_ok = false;
       if (i == j + 1 && i < nt) {
         ok = pivot_row(j, write_ok);
