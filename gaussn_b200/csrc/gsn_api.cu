@@ -78,9 +78,10 @@ struct gsn_problem {
   bool onchip_ok = false;
   gsn::OnchipDev od{};
   int4* d_oc_blk = nullptr; double* d_oc_x = nullptr; double* d_oc_y = nullptr; double* d_oc_yerr2 = nullptr;
-  int* d_oc_img = nullptr; int* d_oc_urow = nullptr; int* d_oc_taboff = nullptr; unsigned char* d_oc_tabs = nullptr;
+  int* d_oc_img = nullptr; int* d_oc_urow = nullptr; int* d_oc_taboff = nullptr; unsigned char* d_oc_tabs = nullptr; unsigned char* d_oc_tabs1 = nullptr;
   std::vector<int> h_oc_urow;
   size_t smem_onchip = 0; int onchip_ctas_smem = 0, onchip_regs = 0;
+  size_t smem_onchip1 = 0; int onchip_ctas_smem1 = 0;   // one-warp teams: smaller live set
   int last_shape = 0;
   int last_warps = 0;     // warps per theta of the most recent on-chip launch
   int n_theta_cols = 0;   // columns the caller's theta must provide
@@ -161,14 +162,18 @@ int dispatch_logl_out_impl(gsn_problem* p, const double* theta, int64_t B, int64
     if (const char* e = getenv("GSN_ONCHIP_WARPS_PER_SM")) target = std::max(1, atoi(e));
     const int t_cap = std::max(1, std::min(gsn::kOnchipMaxWarps, p->od.nt_max / 2));
     int T = (target + p->onchip_ctas_smem - 1) / p->onchip_ctas_smem;
-    if (p->onchip_ctas_smem >= 10) T = 1;     // ten and more one-warp thetas per SM: N = 64 runs 55 M evals/s so, 52 M as teams of two
+    // ten and more one-warp thetas per SM: N = 64 runs 55 M evals/s so, 52 M as teams of two (a one-warp team recycles
+    // tile slots one column earlier, so more of them fit: gsn_onchip.cuh, kOnchipLagOneWarp)
+    int one_warp_min = 12;
+    if (const char* e = getenv("GSN_ONCHIP_ONE_WARP_MIN")) one_warp_min = std::max(1, atoi(e));   // tuning hook
+    if (p->onchip_ctas_smem1 >= one_warp_min) T = 1;
     if (T > 8) T = gsn::kOnchipMaxWarps;
     T = std::max(1, std::min(T, t_cap));
     // few thetas: larger teams shorten the critical path of each
     while (T < t_cap && B * T * 2 <= (int64_t)p->sm_count * 4) T = std::min(t_cap, T * 2);
     if (const char* e = getenv("GSN_ONCHIP_T")) T = std::max(1, std::min(gsn::kOnchipMaxWarps, atoi(e)));
-    const size_t smem = p->smem_onchip;
-    const int ctas_smem = p->onchip_ctas_smem;
+    const size_t smem = (T == 1) ? p->smem_onchip1 : p->smem_onchip;
+    const int ctas_smem = (T == 1) ? p->onchip_ctas_smem1 : p->onchip_ctas_smem;
     int ctas = std::max(1, std::min(std::min(ctas_smem, 32), warps_max / T));
     if (const char* e = getenv("GSN_ONCHIP_CTAS")) ctas = std::max(1, std::min(ctas, atoi(e)));   // tuning hook
     const int grid = (int)std::min<int64_t>(B, (int64_t)p->sm_count * ctas);
@@ -591,20 +596,22 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
     if (const char* e = getenv("GSN_ONCHIP_MAX_ROWS")) max_rows = atoi(e);   // tuning hook; 0 switches the shape off
     const char* shape_env = getenv("GSN_FORCE_SHAPE");                       // any forced legacy shape switches it off as well
     // live-set slot tables, one per distinct block size
-    std::vector<unsigned char> tabs;
+    std::vector<unsigned char> tabs, tabs1;   // teams of several warps / one-warp teams (gsn_onchip.cuh: kOnchipLagOneWarp)
     std::vector<int> tab_off(blk.size(), 0), off_of_nt(gsn::kOnchipMaxTiles + 1, -1);
-    int n_slots = 0;
+    int n_slots = 0, n_slots1 = 0;
     if (nt_max <= gsn::kOnchipMaxTiles)
       for (size_t b = 0; b < blk.size(); ++b) {
         const int nt = blk[b].y;
         if (off_of_nt[nt] < 0) {
           off_of_nt[nt] = (int)tabs.size();
           tabs.resize(tabs.size() + (size_t)nt * (nt + 1) / 2);
+          tabs1.resize(tabs.size());
           n_slots = std::max(n_slots, gsn::onchip_slot_table(nt, tabs.data() + off_of_nt[nt]));
+          n_slots1 = std::max(n_slots1, gsn::onchip_slot_table(nt, tabs1.data() + off_of_nt[nt], gsn::kOnchipLagOneWarp));
         }
         tab_off[b] = off_of_nt[nt];
       }
-    const gsn::OnchipSmem lay(nt_max, n_slots, groups, pd.P, has_aux);
+    const gsn::OnchipSmem lay(nt_max, n_slots, groups, pd.P, has_aux), lay1(nt_max, n_slots1, groups, pd.P, has_aux);
     if (!shape_env && nt_max <= gsn::kOnchipMaxTiles && 8 * nt_max <= max_rows + 7 && (int)blk.size() <= gsn::kOnchipMaxBlocks &&
         lay.bytes <= 226 * 1024) {
       const size_t nr = urow.size();
@@ -623,6 +630,8 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
       GSN_CUDA_P(cudaMalloc(&p->d_oc_urow, sizeof(int) * nr));
       GSN_CUDA_P(cudaMalloc(&p->d_oc_taboff, sizeof(int) * tab_off.size()));
       GSN_CUDA_P(cudaMalloc(&p->d_oc_tabs, tabs.size()));
+      GSN_CUDA_P(cudaMalloc(&p->d_oc_tabs1, tabs1.size()));
+      GSN_CUDA_P(cudaMemcpy(p->d_oc_tabs1, tabs1.data(), tabs1.size(), cudaMemcpyHostToDevice));
       GSN_CUDA_P(cudaMemcpy(p->d_oc_taboff, tab_off.data(), sizeof(int) * tab_off.size(), cudaMemcpyHostToDevice));
       GSN_CUDA_P(cudaMemcpy(p->d_oc_tabs, tabs.data(), tabs.size(), cudaMemcpyHostToDevice));
       GSN_CUDA_P(cudaMemcpy(p->d_oc_blk, blk.data(), sizeof(int4) * blk.size(), cudaMemcpyHostToDevice));
@@ -631,13 +640,15 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
       GSN_CUDA_P(cudaMemcpy(p->d_oc_yerr2, oe.data(), sizeof(double) * nr, cudaMemcpyHostToDevice));
       GSN_CUDA_P(cudaMemcpy(p->d_oc_img, oimg.data(), sizeof(int) * nr, cudaMemcpyHostToDevice));
       GSN_CUDA_P(cudaMemcpy(p->d_oc_urow, urow.data(), sizeof(int) * nr, cudaMemcpyHostToDevice));
-      p->od.n_blocks = (int)blk.size(); p->od.nt_max = nt_max; p->od.n_groups = groups; p->od.n_slots = n_slots;
-      p->od.tab_off = p->d_oc_taboff; p->od.tabs = p->d_oc_tabs;
+      p->od.n_blocks = (int)blk.size(); p->od.nt_max = nt_max; p->od.n_groups = groups; p->od.n_slots = n_slots; p->od.n_slots1 = n_slots1;
+      p->od.tab_off = p->d_oc_taboff; p->od.tabs = p->d_oc_tabs; p->od.tabs1 = p->d_oc_tabs1;
       p->od.blk = p->d_oc_blk; p->od.x = p->d_oc_x; p->od.y = p->d_oc_y; p->od.yerr2 = p->d_oc_yerr2;
       p->od.img = p->d_oc_img; p->od.urow = p->d_oc_urow;
       p->h_oc_urow = urow;
       p->smem_onchip = lay.bytes;
       p->onchip_ctas_smem = std::max(1, (int)((size_t)(227 * 1024) / (lay.bytes + 1024)));
+      p->smem_onchip1 = lay1.bytes;
+      p->onchip_ctas_smem1 = std::max(1, (int)((size_t)(227 * 1024) / (lay1.bytes + 1024)));
       GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_onchip_a(kernel_kind, nullptr, &p->onchip_regs)
                                     : gsn::launch_logl_onchip_b(kernel_kind, nullptr, &p->onchip_regs));
       p->onchip_ok = true;
@@ -657,7 +668,7 @@ int gsn_problem_destroy(gsn_problem* p) {
   cudaFree(p->d_theta_col); cudaFree(p->d_theta_fixed); cudaFree(p->d_workspace); cudaFree(p->d_counter); cudaFree(p->d_items); cudaFree(p->d_items_cluster);
   cudaFree(p->d_theta); cudaFree(p->d_logl); cudaFree(p->d_info);
   cudaFree(p->d_pred_ws); cudaFree(p->d_pred_items);
-  cudaFree(p->d_oc_blk); cudaFree(p->d_oc_x); cudaFree(p->d_oc_y); cudaFree(p->d_oc_yerr2); cudaFree(p->d_oc_img); cudaFree(p->d_oc_urow); cudaFree(p->d_oc_taboff); cudaFree(p->d_oc_tabs);
+  cudaFree(p->d_oc_blk); cudaFree(p->d_oc_x); cudaFree(p->d_oc_y); cudaFree(p->d_oc_yerr2); cudaFree(p->d_oc_img); cudaFree(p->d_oc_urow); cudaFree(p->d_oc_taboff); cudaFree(p->d_oc_tabs); cudaFree(p->d_oc_tabs1);
   if (p->h_theta) cudaFreeHost(p->h_theta);
   if (p->h_logl) cudaFreeHost(p->h_logl);
   if (p->h_info) cudaFreeHost(p->h_info);

@@ -28,7 +28,7 @@
 //                      rides along as row 0 of an extra tile Z, whose "L" is z^T = (L^-1 r)^T
 // A warp sweeps the columns; in column j it first runs T(j+1, j) and D(j+1) back to back if row j+1 is its own
 // (look-ahead: the next column's pivot tile is on the critical path), then its other rows two at a time (two independent
-// accumulator chains per B operand).  Row operands L(i, k) are the warp's own stores; the only cross-warp data are row j
+// accumulator chains per B operand; four at a time: 102 registers, -10 % at N = 64, -16 % at N = 141).  Row operands L(i, k) are the warp's own stores; the only cross-warp data are row j
 // (needed from column j on) and -inv(L(j,j)), z(j).  Two monotone counters in shared memory carry that dataflow:
 // prog_row (rows complete up to their last off-diagonal tile), prog_diag (pivot tiles factored) and prog_z (z stored),
 // release / acquire at CTA scope; the GEMM of T(i, j) only needs prog_row > j, so it overlaps the 8x8 factorisation of D(j)
@@ -47,7 +47,11 @@ namespace gsn {
 #ifndef GSN_ONCHIP_LAG
 #define GSN_ONCHIP_LAG 2
 #endif
-constexpr int kOnchipLag = GSN_ONCHIP_LAG;   // tiles written in column j take the slots of row j - kOnchipLag
+constexpr int kOnchipLag = GSN_ONCHIP_LAG;   // tiles written in column j take the slots of row j - kOnchipLag (teams of several warps)
+// A one-warp team finishes column j - 1 (its last reads of row j - 1) before it stores anything of column j, so its tiles
+// can take the slots of row j - 1 already: 21 slots instead of 25 at N = 64 (15 thetas per SM instead of 13), 7 instead of 9
+// at N = 32.  The host builds both tables; the kernel picks by team size.
+constexpr int kOnchipLagOneWarp = 1;
 constexpr int kOnchipMaxTiles = 28;    // largest band block: 224 rows (225 live tiles = 113 KB; slot numbers fit a byte)
 constexpr int kOnchipDispatchRows = 192;   // band blocks above this run the workspace kernels (N = 224: 2.8 M evals/s here, 3.6 M there)
 constexpr int kOnchipMaxWarps = 16;
@@ -57,10 +61,12 @@ struct OnchipDev {
   int n_blocks;        // band blocks (1 without a band mask)
   int nt_max;          // tile rows of the largest block
   int n_groups;        // 32-row groups over all blocks: granularity of the final reduction
-  int n_slots;         // tile slots of the largest block's live set
+  int n_slots;         // tile slots of the largest block's live set (teams of several warps)
+  int n_slots1;        // ... for a one-warp team (kOnchipLagOneWarp)
   const int4* blk;     // [n_blocks] {first row in the on-chip layout, tile rows, first group, real rows}
   const int* tab_off;  // [n_blocks] offset of the block's slot table in `tabs`
   const unsigned char* tabs;   // slot of tile (i, k) at i(i+1)/2 + k, per distinct block size
+  const unsigned char* tabs1;  // the same for a one-warp team
   const double* x;     // per row of the on-chip layout (bands aligned to 8 rows)
   const double* y;
   const double* yerr2;
@@ -100,14 +106,14 @@ struct OnchipSmem {
 
 // Slot table of a block of nt tile rows: tile (i, k) -> slot, by simulating the schedule.  Phase p (tile column p; p = -1
 // is the first pivot tile) gives birth to the pivot tile (p + 1, p + 1) and the tiles (i, p), i > p; the slots of row
-// p - kOnchipLag are free again from phase p on.  Returns the number of slots.
-inline int onchip_slot_table(int nt, unsigned char* tab) {
+// p - lag are free again from phase p on.  Returns the number of slots.
+inline int onchip_slot_table(int nt, unsigned char* tab, int lag = kOnchipLag) {
   auto tri = [](int i) { return i * (i + 1) / 2; };
   int free_list[kOnchipMaxTiles * (kOnchipMaxTiles + 1) / 2], head = 0, tail = 0, fresh = 0;
   auto take = [&]() { return head < tail ? free_list[head++] : fresh++; };
   for (int p = -1; p < nt - 1; ++p) {
-    if (p >= kOnchipLag)
-      for (int k = 0; k <= p - kOnchipLag; ++k) free_list[tail++] = tab[tri(p - kOnchipLag) + k];
+    if (p >= lag)
+      for (int k = 0; k <= p - lag; ++k) free_list[tail++] = tab[tri(p - lag) + k];
     tab[tri(p + 1) + p + 1] = (unsigned char)take();
     if (p >= 0)
       for (int i = p + 1; i < nt; ++i) tab[tri(i) + p] = (unsigned char)take();
@@ -364,8 +370,10 @@ logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta
                    unsigned* counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
-  const OnchipSmem lay(od.nt_max, od.n_slots, od.n_groups, pd.P, kernel_has_aux<KIND>());
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+  const bool one_warp = (nthreads == 32);
+  const int n_slots = one_warp ? od.n_slots1 : od.n_slots;
+  const OnchipSmem lay(od.nt_max, n_slots, od.n_groups, pd.P, kernel_has_aux<KIND>());
   double* exptab = sm;
   double* th = sm + lay.off_theta;
   double* ldg = sm + lay.off_ldg;
@@ -434,7 +442,7 @@ logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta
         if (kernel_has_aux<KIND>()) aux[n] = ax;
       }
       {
-        const unsigned char* src = od.tabs + od.tab_off[blk];
+        const unsigned char* src = (one_warp ? od.tabs1 : od.tabs) + od.tab_off[blk];
         for (int n = tid; n < nt * (nt + 1) / 2; n += nthreads) tab[n] = src[n];
         for (int n = tid; n < nt; n += nthreads) ctl->cdone[n] = 0;
       }
@@ -442,7 +450,7 @@ logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta
       // Debug build (compute-sanitizer is closed on this pool): every tile slot starts as NaN, so a tile that is read before
       // it was written in THIS block -- a wrong slot table, a missing wait -- turns the result into NaN and fails the parity
       // tests.  Rows whose slots are recycled are poisoned again by whoever recycles them (see may_write).
-      for (int n = tid; n < od.n_slots * 32; n += nthreads)
+      for (int n = tid; n < n_slots * 32; n += nthreads)
         reinterpret_cast<double2*>(sm + lay.off_tiles)[n] = make_double2(__longlong_as_double(0x7ff8dead00000000LL), __longlong_as_double(0x7ff8dead00000000LL));
 #endif
       if (tid == 0) { ctl->prog_row = 1; ctl->prog_diag = 0; ctl->prog_z = 0; }
