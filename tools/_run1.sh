@@ -1,4 +1,5 @@
-for v in 10_6_48_c1 9_7_48_c1 10_6_48_c0; do
-timeout -s KILL 120 ./bench/ozaki_syrk_$v 64 > gpurun_out/ozaki_syrk_$v.json 2> gpurun_out/ozaki_syrk_$v.err; echo "ozaki $v rc=$?"
-cat gpurun_out/ozaki_syrk_$v.json gpurun_out/ozaki_syrk_$v.err | head -5
+for v in shipped accexp sqrtdiv both; do
+  if [ $v = shipped ]; then unset GSN_LIB; else export GSN_LIB=$PWD/variants/$v.so; fi
+  echo "variant $v" >> gpurun_out/arbiter_variants.jsonl
+  SPANS=150 python tools/arbiter_check.py 192 512 >> gpurun_out/arbiter_variants.jsonl 2>> gpurun_out/arbiter_variants.err
 done

@@ -16,6 +16,8 @@ nvcc $F -DGSN_SLICE_CFG=CfgTiny -DGSN_SLICE_NAME=launch_logl_tiny_a -DGSN_SLICE_
 nvcc $F -DGSN_SLICE_CFG=CfgTiny -DGSN_SLICE_NAME=launch_logl_tiny_b -DGSN_SLICE_LO=5 -DGSN_SLICE_HI=10 -c -o $T/tb.o gsn_kernels.cu &
 nvcc $F -DGSN_SLICE_NAME=launch_logl_cluster_a -DGSN_SLICE_LO=0 -DGSN_SLICE_HI=4 -c -o $T/ca.o gsn_cluster.cu &
 nvcc $F -DGSN_SLICE_NAME=launch_logl_cluster_b -DGSN_SLICE_LO=5 -DGSN_SLICE_HI=10 -c -o $T/cb.o gsn_cluster.cu &
+nvcc $F -DGSN_SLICE_NAME=launch_logl_onchip_a -DGSN_SLICE_LO=0 -DGSN_SLICE_HI=4 -c -o $T/oa.o gsn_onchip.cu &
+nvcc $F -DGSN_SLICE_NAME=launch_logl_onchip_b -DGSN_SLICE_LO=5 -DGSN_SLICE_HI=10 -c -o $T/ob.o gsn_onchip.cu &
 nvcc $F -DGSN_SLICE_NAME=launch_predict_a -DGSN_SLICE_LO=0 -DGSN_SLICE_HI=4 -c -o $T/pa.o gsn_predict.cu &
 nvcc $F -DGSN_SLICE_NAME=launch_predict_b -DGSN_SLICE_LO=5 -DGSN_SLICE_HI=10 -c -o $T/pb.o gsn_predict.cu &
 wait
