@@ -217,6 +217,46 @@ def ncu_traffic(N, B):
     return None, "no ncu capture committed for this size"
 
 
+def reference_shapes(local):
+    """The shapes of the reference's own data sets (all small band blocks: the on-chip kernel), device-timed next to the
+    headline so that the round's bench record carries them: the quasar notebook's N = 141 (3 images, OU kernel), the SN
+    notebook's 4 bands x 2 images N = 194 with a Bazin mean, the getting-started shape.  theta resident, 262 144 per launch."""
+    import torch
+    from gaussn_b200 import gausSN, kernels, meanfuncs, lensingmodels, _engine
+    rng = np.random.default_rng(3)
+    A, TAU, C, CM = (0.05, 1.0), (10, 40), (-0.2, 0.2), [(0, 60), (0.1, 1.0)]
+    bazin = [(0.5, 2), (0, 0.2), (20, 40), (25, 50), (4, 10)]
+    shapes = [("quasar notebook shape: N=141, 1 band x 3 images, OUKernel", 141, 1, 3, kernels.OUKernel, [(0.01, 0.3), (50, 400)], meanfuncs.UniformMean, [C], "OUKernel"),
+              ("SN notebook shape: N=194, 4 bands x 2 images, ExpSquaredKernel + Bazin2009", 194, 4, 2, kernels.ExpSquaredKernel, [A, TAU], meanfuncs.Bazin2009, bazin, "ExpSquaredKernel"),
+              ("getting-started shape: N=64, 1 band x 2 images, ExpSquaredKernel", 64, 1, 2, kernels.ExpSquaredKernel, [A, TAU], meanfuncs.UniformMean, [C], "ExpSquaredKernel")]
+    out, Bs = [], 262144
+    peak, _ = fp64_peak()
+    for name, N, nb, ni, kern, kp, mean, mp, kname in shapes:
+        ds = benchdata.make_dataset(N, nb, ni)
+        cols = [rng.uniform(lo, hi, Bs) for lo, hi in kp + mp]
+        for _ in range(ni - 1):
+            cols += [rng.uniform(lo, hi, Bs) for lo, hi in CM]
+        theta = torch.as_tensor(np.column_stack(cols), device=f"cuda:{local}")
+        gp = gausSN.GP(kern([1.0] * len(kp)), mean([1.0] * len(mp)), lensingmodels.ConstantMagnification([1.0] * (2 * (ni - 1))), device=local)
+        gp.x, gp.y, gp.yerr = ds["x"], ds["y"], ds["yerr"]
+        gp._prepare_indices(ds["x"], ds["band"], ds["image"])
+        for _ in range(2):
+            res = gp.loglikelihood_batch(theta)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            res = gp.loglikelihood_batch(theta)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        flops = benchdata.algorithmic_flops(N, nb, True, kname)
+        out.append(dict(workload=name, theta_per_launch=Bs, ms_per_launch=ms, evals_per_s=Bs / ms * 1e3,
+                        frac_of_fp64_peak=flops * Bs / ms / 1e9 / peak, finite_fraction=float(torch.isfinite(res).float().mean()),
+                        kernel="gsn::logl_onchip_kernel" if gp._problem.query(_engine.Q_PATH) == _engine.PATH_ONCHIP else "workspace kernel",
+                        warps_per_theta=int(gp._problem.query(_engine.Q_ONCHIP_WARPS))))
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -388,6 +428,8 @@ def run_own(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         base, ok = parity_legs(args, gausSN, kernels, meanfuncs, lensingmodels, ds, theta_h, out_h, local)
         line["cpu_baseline"] = base
+    if rank == 0 and world == 1:
+        line["reference_data_shapes"] = reference_shapes(local)   # not part of the timed steps above
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = (
     "gsn_mean", "gsn_lens", "gsn_kernel_nparams", "gsn_mean_nparams", "gsn_lens_nparams",
     "gsn_abi_version", "gsn_last_error", "gsn_item_order", "gsn_logl_batch_gather",
     "gsn_predict_batch", "gsn_predict_batch_host", "gsn_predict_item_order", "gsn_problem_set_data",
-    "gsn_measure_fp64_peak", "gsn_device_count",
+    "gsn_measure_fp64_peak", "gsn_device_count", "gsn_onchip_slot_table",
 )
 MAX_ORDER = 8128   # largest padded order of a factorisation (32 * 254 block rows), also for n_rows + M of a prediction
 
@@ -89,6 +89,8 @@ def load():
                                                _dp, _dp, _dp, _dp, _ip]
         lib.gsn_device_count.restype = C.c_int32
         lib.gsn_measure_fp64_peak.argtypes = [C.c_int, C.c_double, _dp]
+        lib.gsn_onchip_slot_table.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_uint8), C.c_int64]
+        lib.gsn_onchip_slot_table.restype = C.c_int64
         lib.gsn_query.argtypes = [C.c_void_p, C.c_int32]
         lib.gsn_query.restype = C.c_int64
         lib.gsn_covariance.argtypes = [C.c_int, C.c_int32, _dp, C.c_int32, _dp, C.c_int64, _dp, C.c_int64, _dp]
@@ -130,6 +132,17 @@ def default_device() -> int:
         n = int(load().gsn_device_count())
         return int(rank) % n if n > 0 else int(rank)
     return 0
+
+
+def onchip_slot_table(tile_rows: int, lag: int):
+    """(slots, table) of the on-chip shape's recycled tile storage: tile (i, k) lives in slot table[i (i + 1) / 2 + k]."""
+    import numpy as np
+    n = tile_rows * (tile_rows + 1) // 2
+    tab = np.zeros(n, dtype=np.uint8)
+    slots = load().gsn_onchip_slot_table(tile_rows, lag, tab.ctypes.data_as(C.POINTER(C.c_uint8)), n)
+    if slots < 0:
+        raise GsnError(f"gsn_onchip_slot_table({tile_rows}, {lag}): bad arguments")
+    return int(slots), tab
 
 
 def measure_fp64_peak(device=None, seconds=0.3) -> float:

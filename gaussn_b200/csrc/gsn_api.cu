@@ -969,6 +969,14 @@ static int open_device(int device) {
   return GSN_OK;
 }
 
+int64_t gsn_onchip_slot_table(int32_t tile_rows, int32_t lag, uint8_t* out, int64_t cap) {
+  if (tile_rows < 1 || tile_rows > gsn::kOnchipMaxTiles || lag < 1 || lag > 4) return -1;
+  std::vector<unsigned char> tab((size_t)tile_rows * (tile_rows + 1) / 2);
+  const int n_slots = gsn::onchip_slot_table(tile_rows, tab.data(), lag);
+  if (out && cap >= (int64_t)tab.size()) std::copy(tab.begin(), tab.end(), out);
+  return n_slots;
+}
+
 int gsn_measure_fp64_peak(int device, double seconds, double* tflops_out) {
   if (!tflops_out) return fail(GSN_ERR_INVALID, "tflops_out is null");
   if (int rc = open_device(device)) return rc;

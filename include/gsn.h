@@ -231,6 +231,14 @@ int gsn_measure_fp64_peak(int device, double seconds, double* tflops_out);
  * (lensingmodels.py:39-51) makes identically zero are not listed. */
 int64_t gsn_item_order(int64_t N, const int32_t* band_of_row, int32_t n_bands, int32_t masked, uint32_t* out, int64_t cap);
 
+/* Introspection, no device needed: the tile-slot table of the on-chip shape (gsn_onchip.cuh) for a band block of
+ * `tile_rows` 8-row tile rows.  The factor's 8x8 tiles live in recycled shared-memory slots: tile (i, k), k <= i, of the
+ * lower triangle is held in slot out[i (i + 1) / 2 + k]; the tiles of row r are dead `lag` tile columns after column r
+ * (lag 2 for teams of several warps, 1 for a one-warp team) and their slots are handed to the tiles born then.  Returns the
+ * number of slots (also when out is NULL or cap is too small), -1 on bad arguments.  tests/test_host_logic.py replays the
+ * schedule against this table: no tile may take a slot whose previous tenant can still be read. */
+int64_t gsn_onchip_slot_table(int32_t tile_rows, int32_t lag, uint8_t* out, int64_t cap);
+
 /* The same for gsn_predict_batch with n_rows conditioning epochs and M prediction epochs: items of the augmented matrix
  * (n_rows padded to 32, then the M epochs).  Bit 23 of a word marks a trailing block (both c and j among the prediction
  * rows: accumulated and written out, neither solved nor factored); c = (word >> 12) & 0x7ff, j = word & 0xfff. */

@@ -313,3 +313,36 @@ def test_batched_finite_difference_gradient_matches_the_analytic_one():
     spy = Spy(gp, None, False, False, False, invert=-1)
     samplers.fd_value_and_grad(spy, theta, bounds=bounds)
     assert np.all(used[1:, 0] <= 0.3) and np.all(used[:, 2] <= 5.0) and np.all(used[:, 3] >= 0.0)
+
+
+@pytest.mark.parametrize("lag", [1, 2])
+def test_onchip_tile_slots_are_never_handed_over_while_their_tenant_is_live(libgsn, lag):
+    """The on-chip shape keeps only the live part of the factor: tile (i, k) sits in a recycled shared-memory slot
+    (gsn_onchip.cuh).  A left-looking sweep reads the tiles of row r for the last time in tile column r, and the kernel lets
+    a warp store into column p only when every warp has left column p - lag (one-warp teams: lag 1, the warp's own program
+    order).  So the table is safe iff, for every slot, a tenant born in phase p replaces a tile of a row <= p - lag -- replayed
+    here for every block size the kernel accepts (compute-sanitizer cannot be run on this pool; this is the host-side half
+    of its job, the device-side half is the NaN-poisoned build of tests/test_gpu_onchip.py)."""
+    from gaussn_b200 import _engine
+
+    def birth(i, k):            # phase (tile column in work) in which tile (i, k) is first written; -1: the first pivot tile
+        return k if i > k else i - 1
+
+    for nt in range(1, 29):
+        n_slots, tab = _engine.onchip_slot_table(nt, lag)
+        tenants = {}
+        for i in range(nt):
+            for k in range(i + 1):
+                slot = int(tab[i * (i + 1) // 2 + k])
+                assert 0 <= slot < n_slots
+                tenants.setdefault(slot, []).append((birth(i, k), i, k))
+        assert len(tenants) == n_slots                                  # no slot is counted but unused
+        for slot, ts in tenants.items():
+            ts.sort()
+            for (p0, i0, k0), (p1, i1, k1) in zip(ts, ts[1:]):
+                assert p1 > p0, f"nt={nt}: tiles ({i0},{k0}) and ({i1},{k1}) are born in the same phase into slot {slot}"
+                assert i0 <= p1 - lag, f"nt={nt}: tile ({i1},{k1}) takes slot {slot} in phase {p1} while row {i0} is still read"
+        live_max = max(sum(1 for i in range(nt) for k in range(i + 1) if birth(i, k) <= p and i > p - lag) for p in range(-1, nt - 1))
+        assert n_slots >= live_max                                       # cannot be smaller than the largest live set
+    assert _engine.onchip_slot_table(18, 2)[0] == 100 and _engine.onchip_slot_table(18, 1)[0] == 91    # N = 141 (DESIGN.md section 3a)
+    assert _engine.onchip_slot_table(8, 2)[0] == 25 and _engine.onchip_slot_table(8, 1)[0] == 21       # N = 64

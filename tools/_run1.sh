@@ -1,5 +1,3 @@
-for v in shipped accexp sqrtdiv both; do
-  if [ $v = shipped ]; then unset GSN_LIB; else export GSN_LIB=$PWD/variants/$v.so; fi
-  echo "variant $v" >> gpurun_out/arbiter_variants.jsonl
-  SPANS=150 python tools/arbiter_check.py 192 512 >> gpurun_out/arbiter_variants.jsonl 2>> gpurun_out/arbiter_variants.err
-done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py --steps 5 --warmup 3 --peaks > gpurun_out/bench_r02_s2.json 2> gpurun_out/bench_r02_s2.err; echo "bench rc=$?"
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -6
