@@ -81,6 +81,8 @@ struct gsn_problem {
   int* d_oc_img = nullptr; int* d_oc_urow = nullptr; int* d_oc_taboff = nullptr; unsigned char* d_oc_tabs = nullptr; unsigned char* d_oc_tabs1 = nullptr;
   std::vector<int> h_oc_urow;
   size_t smem_onchip = 0; int onchip_ctas_smem = 0, onchip_regs = 0;
+  int onchip_regs2[2] = {0, 0};                          // shared-memory shape, register shape
+  bool onchip_reg_ok = false; size_t smem_onchip_reg = 0;   // band blocks of at most kRegMaxTiles tile rows: factor in registers
   size_t smem_onchip1 = 0; int onchip_ctas_smem1 = 0;   // one-warp teams: smaller live set
   int last_shape = 0;
   int last_warps = 0;     // warps per theta of the most recent on-chip launch
@@ -172,14 +174,18 @@ int dispatch_logl_out_impl(gsn_problem* p, const double* theta, int64_t B, int64
     // few thetas: larger teams shorten the critical path of each
     while (T < t_cap && B * T * 2 <= (int64_t)p->sm_count * 4) T = std::min(t_cap, T * 2);
     if (const char* e = getenv("GSN_ONCHIP_T")) T = std::max(1, std::min(gsn::kOnchipMaxWarps, atoi(e)));
-    const size_t smem = (T == 1) ? p->smem_onchip1 : p->smem_onchip;
-    const int ctas_smem = (T == 1) ? p->onchip_ctas_smem1 : p->onchip_ctas_smem;
+    // Blocks of at most 64 rows, one warp per theta: the factor stays in registers (gsn_onchip.cuh, reg_factor)
+    bool reg = p->onchip_reg_ok && T == 1;
+    if (const char* e = getenv("GSN_ONCHIP_REG")) reg = reg && atoi(e) != 0;   // tuning hook / tests: 0 forces the shared-memory shape
+    const size_t smem = reg ? p->smem_onchip_reg : (T == 1) ? p->smem_onchip1 : p->smem_onchip;
+    const int ctas_smem = reg ? (int)((size_t)(227 * 1024) / (p->smem_onchip_reg + 1024)) : (T == 1) ? p->onchip_ctas_smem1 : p->onchip_ctas_smem;
     int ctas = std::max(1, std::min(std::min(ctas_smem, 32), warps_max / T));
+    if (reg) ctas = std::max(1, std::min(std::min(ctas_smem, 32), 65536 / (((p->onchip_regs2[1] + 7) / 8 * 8) * 32)));
     if (const char* e = getenv("GSN_ONCHIP_CTAS")) ctas = std::max(1, std::min(ctas, atoi(e)));   // tuning hook
     const int grid = (int)std::min<int64_t>(B, (int64_t)p->sm_count * ctas);
     p->last_shape = GSN_PATH_ONCHIP;
     p->last_warps = T;
-    gsn::OnchipLaunchArgs a{p->pd, p->od, theta, B, ld, hostmean, out, info, flags, p->d_counter, grid, T, smem, stream};
+    gsn::OnchipLaunchArgs a{p->pd, p->od, theta, B, ld, hostmean, out, info, flags, p->d_counter, grid, T, smem, stream, reg};
     const cudaError_t e = (k <= 4) ? gsn::launch_logl_onchip_a(k, &a, nullptr) : gsn::launch_logl_onchip_b(k, &a, nullptr);
     if (e != cudaSuccess) return fail(GSN_ERR_CUDA, "on-chip log-likelihood kernel launch failed: %s", cudaGetErrorString(e));
     p->launches += 1;
@@ -649,8 +655,11 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
       p->onchip_ctas_smem = std::max(1, (int)((size_t)(227 * 1024) / (lay.bytes + 1024)));
       p->smem_onchip1 = lay1.bytes;
       p->onchip_ctas_smem1 = std::max(1, (int)((size_t)(227 * 1024) / (lay1.bytes + 1024)));
-      GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_onchip_a(kernel_kind, nullptr, &p->onchip_regs)
-                                    : gsn::launch_logl_onchip_b(kernel_kind, nullptr, &p->onchip_regs));
+      GSN_CUDA_P((kernel_kind <= 4) ? gsn::launch_logl_onchip_a(kernel_kind, nullptr, p->onchip_regs2)
+                                    : gsn::launch_logl_onchip_b(kernel_kind, nullptr, p->onchip_regs2));
+      p->onchip_regs = p->onchip_regs2[0];
+      p->onchip_reg_ok = nt_max <= gsn::kRegMaxTiles;
+      p->smem_onchip_reg = gsn::OnchipSmem(nt_max, 0, groups, pd.P, has_aux).bytes;
       p->onchip_ok = true;
     }
   }

@@ -55,8 +55,9 @@ struct OnchipLaunchArgs {
   int warps;          // warps per theta (= CTA size / 32): 1, 2, 4, 8 or 16
   size_t smem_bytes;
   cudaStream_t stream;
+  bool reg = false;   // one warp per theta with the factor in registers (band blocks of at most kRegMaxTiles tile rows)
 };
-// a == nullptr prepares the kernel and reports its register count.
+// a == nullptr prepares the kernels and reports their register counts: regs[0] the shared-memory shape, regs[1] the register shape.
 cudaError_t launch_logl_onchip_a(int kind, const OnchipLaunchArgs* a, int* regs);   // kinds 0..4
 cudaError_t launch_logl_onchip_b(int kind, const OnchipLaunchArgs* a, int* regs);   // kinds 5..10
 

@@ -12,15 +12,18 @@ static cudaError_t prepare_one(int* regs) {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (!attr_set[dev & 63]) {
-    e = cudaFuncSetAttribute(logl_onchip_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    e = cudaFuncSetAttribute(logl_onchip_kernel<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
   if (regs) {
     cudaFuncAttributes fa;
-    e = cudaFuncGetAttributes(&fa, logl_onchip_kernel<KIND>);
+    e = cudaFuncGetAttributes(&fa, logl_onchip_kernel<KIND, false>);
     if (e != cudaSuccess) return e;
-    *regs = fa.numRegs;
+    regs[0] = fa.numRegs;
+    e = cudaFuncGetAttributes(&fa, logl_onchip_kernel<KIND, true>);
+    if (e != cudaSuccess) return e;
+    regs[1] = fa.numRegs;
   }
   return cudaSuccess;
 }
@@ -29,8 +32,12 @@ template <int KIND>
 static cudaError_t launch_one(const OnchipLaunchArgs& a) {
   cudaError_t e = prepare_one<KIND>(nullptr);
   if (e != cudaSuccess) return e;
-  logl_onchip_kernel<KIND><<<a.grid, a.warps * 32, a.smem_bytes, a.stream>>>(a.pd, a.od, a.theta, a.B, a.ld, a.hostmean, a.out, a.info,
-                                                                             a.flags, a.counter);
+  if (a.reg)
+    logl_onchip_kernel<KIND, true><<<a.grid, 32, a.smem_bytes, a.stream>>>(a.pd, a.od, a.theta, a.B, a.ld, a.hostmean, a.out, a.info,
+                                                                           a.flags, a.counter);
+  else
+    logl_onchip_kernel<KIND, false><<<a.grid, a.warps * 32, a.smem_bytes, a.stream>>>(a.pd, a.od, a.theta, a.B, a.ld, a.hostmean, a.out,
+                                                                                      a.info, a.flags, a.counter);
   return cudaGetLastError();
 }
 

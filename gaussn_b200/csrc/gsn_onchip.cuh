@@ -363,8 +363,155 @@ struct OnchipTeam {
   }
 };
 
+// Band blocks of at most kRegMaxTiles tile rows (64 rows: the getting-started shape, the SN notebook's four bands of 48-49
+// rows) factored by ONE warp with the factor in REGISTERS.  The universal tile layout lets an accumulator tile be fed back
+// as an operand as it is, so the left-looking sweep of OnchipTeam needs no storage at all once its loops are unrolled over a
+// compile-time block size: tile (i, k) is a register pair per lane, the compiler's liveness analysis does what the slot
+// table does for the shared-memory shape, and every load, store, slot lookup and loop counter of the sweep disappears
+// (N = 64: 9 500 instructions per theta through shared memory; 56 -> 65 M evals/s, the SN notebook's shape 20 -> 21.6 M).  All rows of a tile column are swept together (up to six
+// independent accumulator chains, and as many exponentials in flight in the build).  The arithmetic per tile and its
+// order are those of OnchipTeam::pivot_row / panel: results are bit-identical (tests/test_gpu_onchip.py).
+constexpr int kRegMaxTiles = 8;
+#ifndef GSN_REG_CTAS
+#define GSN_REG_CTAS 16            // one-warp CTAs per SM the register shape is compiled for: 128 registers, 8 bytes of spills
+                                   // (12 CTAs / 154 registers: N = 32 167 M against 181 M evals/s; 20 CTAs / 96 registers: 123 M)
+#endif
+constexpr int kRegCtasPerSm = GSN_REG_CTAS;
+
+#ifndef GSN_REG_CALL_CHOL
+#define GSN_REG_CALL_CHOL 1        // the 8x8 pivot routine as one out-of-line copy (the unrolled sweep would inline it up to 36 times)
+#endif
+#ifndef GSN_REG_CALL_BUILD
+#define GSN_REG_CALL_BUILD 0       // ... but not the covariance build of a tile (the call costs more than the instruction cache misses: N = 64 52 M against 64 M evals/s)
+#endif
+static __device__ __noinline__ Chol8Out chol8_inv_onchip_call(double2 a, int lane) {
+  Chol8Out o;
+  o.mant = 1.0; o.expo = 0; o.failrow = -1;
+  chol8_inv_warp<GSN_ONCHIP_DIAG_TILE>(a, lane, o.nW, o.mant, o.expo, o.failrow);
+  return o;
+}
 template <int KIND>
-__global__ void __launch_bounds__(kOnchipMaxWarps * 32, 1)
+static __device__ __noinline__ double2 onchip_build_call(const OnchipTeam<KIND>* tm, int i, int j) {
+  return tm->build(i, j, tm->load_cols(j));
+}
+template <int KIND>
+__device__ __forceinline__ double2 reg_build(const OnchipTeam<KIND>& tm, int i, int j, const typename OnchipTeam<KIND>::Cols& q) {
+#if GSN_REG_CALL_BUILD
+  return onchip_build_call<KIND>(&tm, i, j);
+#else
+  return tm.build(i, j, q);
+#endif
+}
+
+template <int KIND, int NT>
+__device__ __forceinline__ void reg_factor(const OnchipTeam<KIND>& tm) {
+  using Cols = typename OnchipTeam<KIND>::Cols;
+  const int lane = tm.lane;
+  double2 L[NT][NT];   // L[i][k], k < i: the factor's tile; L[i][i]: -inv(L(i, i))
+#pragma unroll
+  for (int j = -1; j < NT - 1; ++j) {
+    const int i = j + 1;
+    // ---- T(j + 1, j) and D(j + 1): OnchipTeam::pivot_row
+    {
+      const Cols qi = tm.load_cols(i);
+      double2 S = make_double2(0.0, 0.0), X = make_double2(0.0, 0.0);
+      double2 D = reg_build<KIND>(tm, i, i, qi);
+      double y = 0.0;
+      if (j >= 0) {
+        S = reg_build<KIND>(tm, i, j, tm.load_cols(j));
+#pragma unroll
+        for (int k = 0; k < j; ++k) {
+          const double2 a = L[i][k], b = L[j][k];
+          const double2 z = tm.zpair(k);
+          dmma(S, a.x, b.x);
+          dmma(D, a.x, a.x);
+          dmma(S, a.y, b.y);
+          dmma(D, a.y, a.y);
+          y = OnchipTeam<KIND>::ydot(y, a, z);
+        }
+        const double2 nWj = L[j][j];
+        dmma(X, S.x, nWj.x);
+        dmma(X, S.y, nWj.y);
+        L[i][j] = X;
+        dmma(D, X.x, X.x);
+        dmma(D, X.y, X.y);
+      }
+      double mant = 1.0;
+      int expo = 0, failrow = -1;
+      double2 nW;
+#if GSN_REG_CALL_CHOL
+      {
+        const Chol8Out o = chol8_inv_onchip_call(make_double2(-D.x, -D.y), lane);
+        nW = o.nW; mant = o.mant; expo = o.expo; failrow = o.failrow;
+      }
+#else
+      chol8_inv_warp<GSN_ONCHIP_DIAG_TILE>(make_double2(-D.x, -D.y), lane, nW, mant, expo, failrow);
+#endif
+      L[i][i] = nW;
+      if (j >= 0) y = OnchipTeam<KIND>::ydot(y, X, tm.zpair(j));
+      tm.finish_z(i, y, nW);
+      if (lane == 0) {
+        if (failrow >= 0) {
+          const int u = tm.urow[8 * i + failrow];
+          atomicCAS(&tm.ctl->fail, 0, u >= 0 ? u + 1 : tm.n_total);
+        }
+        if ((i & 3) != 0) { mant *= tm.ctl->gmant[i >> 2]; expo += tm.ctl->gexpo[i >> 2]; }
+        tm.ctl->gmant[i >> 2] = mant;
+        tm.ctl->gexpo[i >> 2] = expo;
+      }
+      __syncwarp();
+    }
+    // ---- the other rows of tile column j, all at once: OnchipTeam::panel
+    if (j >= 0 && j + 2 < NT) {
+      const Cols q = tm.load_cols(j);
+      double2 S[NT];
+#pragma unroll
+      for (int r = j + 2; r < NT; ++r) S[r] = reg_build<KIND>(tm, r, j, q);
+#pragma unroll
+      for (int k = 0; k < j; ++k) {
+        const double2 b = L[j][k];
+#pragma unroll
+        for (int r = j + 2; r < NT; ++r) dmma(S[r], L[r][k].x, b.x);
+#pragma unroll
+        for (int r = j + 2; r < NT; ++r) dmma(S[r], L[r][k].y, b.y);
+      }
+      const double2 nW = L[j][j];
+#pragma unroll
+      for (int r = j + 2; r < NT; ++r) {
+        double2 X = make_double2(0.0, 0.0);
+        dmma(X, S[r].x, nW.x);
+        dmma(X, S[r].y, nW.y);
+        L[r][j] = X;
+      }
+    }
+  }
+}
+
+#ifndef GSN_REG_MAXNT
+#define GSN_REG_MAXNT 8
+#endif
+template <int KIND>
+__device__ __forceinline__ void reg_factor_any(const OnchipTeam<KIND>& tm, int nt) {
+  switch (nt) {
+    case 1: reg_factor<KIND, 1>(tm); break;
+    case 2: reg_factor<KIND, 2>(tm); break;
+    case 3: reg_factor<KIND, 3>(tm); break;
+    case 4: reg_factor<KIND, 4>(tm); break;
+#if GSN_REG_MAXNT >= 6
+    case 5: reg_factor<KIND, 5>(tm); break;
+    case 6: reg_factor<KIND, 6>(tm); break;
+#endif
+#if GSN_REG_MAXNT >= 7
+    case 7: reg_factor<KIND, 7>(tm); break;
+#endif
+#if GSN_REG_MAXNT >= 8
+    default: reg_factor<KIND, 8>(tm); break;
+#endif
+  }
+}
+
+template <int KIND, bool kReg>
+__global__ void __launch_bounds__(kReg ? 32 : kOnchipMaxWarps * 32, kReg ? kRegCtasPerSm : 1)
 logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta, long long B, long long ld,
                    const double* __restrict__ hostmean, GatherOut out, int* __restrict__ info, unsigned flags,
                    unsigned* counter) {
@@ -372,7 +519,7 @@ logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta
   double* sm = reinterpret_cast<double*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
   const bool one_warp = (nthreads == 32);
-  const int n_slots = one_warp ? od.n_slots1 : od.n_slots;
+  const int n_slots = kReg ? 0 : (one_warp ? od.n_slots1 : od.n_slots);
   const OnchipSmem lay(od.nt_max, n_slots, od.n_groups, pd.P, kernel_has_aux<KIND>());
   double* exptab = sm;
   double* th = sm + lay.off_theta;
@@ -441,7 +588,7 @@ logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta
         xs[n] = x_s; bs[n] = b; rs[n] = r; e2[n] = e;
         if (kernel_has_aux<KIND>()) aux[n] = ax;
       }
-      {
+      if constexpr (!kReg) {
         const unsigned char* src = (one_warp ? od.tabs1 : od.tabs) + od.tab_off[blk];
         for (int n = tid; n < nt * (nt + 1) / 2; n += nthreads) tab[n] = src[n];
         for (int n = tid; n < nt; n += nthreads) ctl->cdone[n] = 0;
@@ -461,7 +608,7 @@ logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta
       team.trace_on = (blockIdx.x == 0 && blk == 0 && n_done == GSN_ONCHIP_TRACE);
       if (team.trace_on && tid == 0) { g_onchip_trace[0] = clock64(); g_onchip_trace[1] = nt; }
 #endif
-      team.factor(warp);
+      if constexpr (kReg) reg_factor_any<KIND>(team, nt); else team.factor(warp);
       __syncthreads();
 #ifdef GSN_ONCHIP_TRACE
       if (team.trace_on && tid == 0) g_onchip_trace[2] = clock64();
