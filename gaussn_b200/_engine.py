@@ -21,7 +21,7 @@ L_NONE, L_CONSTANT, L_SIGMOID, L_SINUSOIDAL = range(4)
 FLAG_NEG_INF = 1
 Q_N, Q_NPARAMS, Q_NPARAMS_KERNEL, Q_NPARAMS_MEAN, Q_NPARAMS_LENS, Q_WORKSPACE_BYTES, Q_GRID, Q_DEVICE, Q_LAUNCHES, Q_NPAD, Q_PATH = range(11)
 Q_CLUSTER2_MAX, Q_CLUSTER4_MAX, Q_CLUSTER8_MAX = 11, 12, 13
-Q_ONCHIP, Q_ONCHIP_WARPS, Q_ONCHIP_SMEM = 14, 15, 16
+Q_ONCHIP, Q_ONCHIP_WARPS, Q_ONCHIP_SMEM, Q_ONCHIP_REG = 14, 15, 16, 17
 PATH_WIDE, PATH_NARROW, PATH_CLUSTER, PATH_ONCHIP = 1, 2, 3, 4
 ABI_VERSION = 1
 

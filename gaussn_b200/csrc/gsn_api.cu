@@ -86,6 +86,7 @@ struct gsn_problem {
   size_t smem_onchip1 = 0; int onchip_ctas_smem1 = 0;   // one-warp teams: smaller live set
   int last_shape = 0;
   int last_warps = 0;     // warps per theta of the most recent on-chip launch
+  bool last_reg = false;  // ... and whether it kept the factor in registers
   int n_theta_cols = 0;   // columns the caller's theta must provide
   // host staging for gsn_logl_batch_host
   double* h_theta = nullptr; double* h_logl = nullptr; int* h_info = nullptr;
@@ -160,7 +161,9 @@ int dispatch_logl_out_impl(gsn_problem* p, const double* theta, int64_t B, int64
     // Team size: enough warps per SM to hide latency (about 15), given how many thetas the shared memory holds -- more thetas
     // in flight beat larger teams (N = 160: 7.7 M evals/s as 3 thetas x 5 warps, 7.1 M as 2 x 8; N = 141: 11.0 M as 3 x 5,
     // 10.5 M as 3 x 4, 9.6 M as 3 x 6) -- and never more warps than half the tile rows; a team may have any size up to 16.
-    int target = 15;
+    // With four or more thetas per SM a fifth warp per team still pays (N = 141: 11.06 M as 4 x 5, 10.52 M as 4 x 4; N = 128:
+    // 13.9 against 13.3 M; three bands of 132 rows: 4.08 against 3.89 M); with two or three the registers cap the SM at 21 warps.
+    int target = p->onchip_ctas_smem >= 4 ? 18 : 15;
     if (const char* e = getenv("GSN_ONCHIP_WARPS_PER_SM")) target = std::max(1, atoi(e));
     const int t_cap = std::max(1, std::min(gsn::kOnchipMaxWarps, p->od.nt_max / 2));
     int T = (target + p->onchip_ctas_smem - 1) / p->onchip_ctas_smem;
@@ -185,6 +188,7 @@ int dispatch_logl_out_impl(gsn_problem* p, const double* theta, int64_t B, int64
     const int grid = (int)std::min<int64_t>(B, (int64_t)p->sm_count * ctas);
     p->last_shape = GSN_PATH_ONCHIP;
     p->last_warps = T;
+    p->last_reg = reg;
     gsn::OnchipLaunchArgs a{p->pd, p->od, theta, B, ld, hostmean, out, info, flags, p->d_counter, grid, T, smem, stream, reg};
     const cudaError_t e = (k <= 4) ? gsn::launch_logl_onchip_a(k, &a, nullptr) : gsn::launch_logl_onchip_b(k, &a, nullptr);
     if (e != cudaSuccess) return fail(GSN_ERR_CUDA, "on-chip log-likelihood kernel launch failed: %s", cudaGetErrorString(e));
@@ -1037,6 +1041,7 @@ int64_t gsn_query(const gsn_problem* p, int32_t what) {
     case GSN_Q_ONCHIP: return p->onchip_ok ? 1 : 0;
     case GSN_Q_ONCHIP_WARPS: return p->last_warps;
     case GSN_Q_ONCHIP_SMEM: return (int64_t)p->smem_onchip;
+    case GSN_Q_ONCHIP_REG: return p->last_reg ? 1 : 0;
   }
   return -1;
 }

@@ -108,7 +108,8 @@ typedef enum gsn_query_what {
   GSN_Q_CLUSTER8_MAX = 13,
   GSN_Q_ONCHIP = 14,         /* 1 if the handle's batch calls run with the factor resident in shared memory (GSN_PATH_ONCHIP) */
   GSN_Q_ONCHIP_WARPS = 15,   /* warps that shared one theta in the most recent such launch */
-  GSN_Q_ONCHIP_SMEM = 16     /* bytes of shared memory one theta occupies in that shape */
+  GSN_Q_ONCHIP_SMEM = 16,    /* bytes of shared memory one theta occupies in that shape */
+  GSN_Q_ONCHIP_REG = 17      /* 1 if the most recent such launch kept the factor in registers (band blocks of at most 64 rows, one warp per theta) */
 } gsn_query_what;
 
 typedef enum gsn_path {

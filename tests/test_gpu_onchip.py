@@ -190,3 +190,31 @@ def test_repeated_runs_with_every_team_size_are_bit_identical(libgsn, monkeypatc
         for rep in range(25):
             got = gp.loglikelihood_batch(theta)
             assert np.array_equal(got, ref, equal_nan=True), f"T={T} repetition {rep}: {int(np.sum(got != ref))} values differ"
+
+
+@pytest.mark.parametrize("kernel", ["ExpSquaredKernel", "Matern32Kernel", "OUKernel", "GibbsKernel", "PeriodicKernel", "JJKernel"])
+@pytest.mark.parametrize("n_bands,n_images,N", [(1, 1, 5), (1, 2, 12), (1, 2, 20), (1, 3, 30), (1, 2, 40), (1, 2, 47), (1, 2, 56),
+                                                (1, 2, 64), (4, 2, 194), (7, 1, 100)])
+def test_register_shape_is_bit_identical_to_the_shared_memory_shape(libgsn, monkeypatch, kernel, n_bands, n_images, N):
+    """Band blocks of at most 64 rows, one warp per theta: the factor lives in registers (reg_factor, every unrolled block
+    size 1 ... 8 tile rows is hit here, alone and mixed within one theta).  Same tile arithmetic in the same order as the
+    shared-memory sweep: the same bits, failures included; and the oracle's values."""
+    from gaussn_b200 import _engine
+    rng = np.random.default_rng(9000 + 31 * N + n_bands)
+    ds = _synth(rng, N, n_bands, n_images)
+    theta = _theta_box(rng, 1200, kernel, "UniformMean", "ConstantMagnification", n_images)   # enough thetas for one-warp teams
+    theta[3, 0] = np.nan
+    theta[7, 1] = np.inf
+    gp = _gp_for(ds, kernel, "UniformMean", "ConstantMagnification", n_images, theta[0])
+    gp.loglikelihood_batch(theta[:2])                           # programs the handle and the theta map
+    got, info = gp._problem.logl_host(theta, 0, return_info=True)
+    assert gp._problem.query(_engine.Q_PATH) == _engine.PATH_ONCHIP and gp._problem.query(_engine.Q_ONCHIP_REG) == 1
+    assert gp._problem.query(_engine.Q_ONCHIP_WARPS) == 1
+    monkeypatch.setenv("GSN_ONCHIP_REG", "0")
+    want, info0 = gp._problem.logl_host(theta, 0, return_info=True)
+    assert gp._problem.query(_engine.Q_ONCHIP_REG) == 0
+    monkeypatch.delenv("GSN_ONCHIP_REG")
+    assert np.array_equal(got, want, equal_nan=True) and np.array_equal(info, info0)
+    assert not np.isfinite(got[3]) and np.isfinite(got).sum() >= 1100      # (an infinite length scale can be a valid model)
+    sel = np.r_[0:3, 4:40, 1150:1200]
+    assert_logl_close(got[sel], _oracle_batch(ds, theta[sel], kernel, "UniformMean", "ConstantMagnification", gp), f"register shape {kernel} N={N}")
