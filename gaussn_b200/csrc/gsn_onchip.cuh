@@ -382,7 +382,8 @@ constexpr int kRegCtasPerSm = GSN_REG_CTAS;
 #define GSN_REG_CALL_CHOL 1        // the 8x8 pivot routine as one out-of-line copy (the unrolled sweep would inline it up to 36 times)
 #endif
 #ifndef GSN_REG_CALL_BUILD
-#define GSN_REG_CALL_BUILD 0       // ... but not the covariance build of a tile (the call costs more than the instruction cache misses: N = 64 52 M against 64 M evals/s)
+#define GSN_REG_CALL_BUILD 0       // ... but not the covariance build of a tile (the call costs more than the instruction cache misses: N = 64 52 M
+                                   // against 64 M evals/s; one out-of-line loop per tile column, results handed over through shared memory: 47 M)
 #endif
 static __device__ __noinline__ Chol8Out chol8_inv_onchip_call(double2 a, int lane) {
   Chol8Out o;
