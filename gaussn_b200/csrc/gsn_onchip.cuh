@@ -42,7 +42,13 @@
 namespace gsn {
 
 #ifndef GSN_ONCHIP_DIAG_TILE
-#define GSN_ONCHIP_DIAG_TILE true    // pivots from the broadcast diagonal tile (see chol8_inv_warp): N = 64 56 M evals/s against 46 M by shuffle
+// Pivots by one shuffle from the tile's own diagonal (see chol8_inv_warp): ten DMMAs fewer per pivot tile, 18 cycles more per
+// pivot.  With the register shape and five-warp teams the FP64 pipe, not the pivot chain, is the scarcer resource: N = 64
+// 64.6 -> 71.0 M evals/s, N = 32 181 -> 204 M, the SN notebook's shape 21.6 -> 24.6 M, N = 141 11.06 -> 11.28 M (the one-warp
+// shared-memory shape of early round 2 lost 18 % to it; the workspace kernels keep the broadcast diagonal tile: N = 512
+// 525 k against 517 k).  The two families therefore differ in the last bits of a pivot (a[c][c] updated by fma against
+// a[c][c] - sum round(L[c][k]^2)); tests hold them to 1e-9 + 1e-13 |logL| of each other.
+#define GSN_ONCHIP_DIAG_TILE false
 #endif
 #ifndef GSN_ONCHIP_LAG
 #define GSN_ONCHIP_LAG 2

@@ -1,3 +1,5 @@
-python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/plain_bench3.log 2>&1; echo "plain rc=$?"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_ncu_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_l3.log 2>&1; echo "ncu rc=$?"
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r02_ref3.json 2> gpurun_out/bench_r02_ref3.err; echo "ref rc=$?"
+python -m pytest tests/test_gpu_onchip.py -x -q 2>&1 | tail -2
+python tools/sweep.py 8 16 32 48 64 80 96 112 128 141 160 176 192 > gpurun_out/r02_sweep_small.jsonl 2>&1
+python tools/sweep_configs.py > gpurun_out/r02_sweep_configs.jsonl 2>&1
+python tools/latency_probe.py > gpurun_out/r02_latency.jsonl 2>&1
+for c in 12 20; do :; done
