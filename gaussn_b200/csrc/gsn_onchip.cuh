@@ -49,6 +49,11 @@ namespace gsn {
 // 525 k against 517 k).  The two families therefore differ in the last bits of a pivot (a[c][c] updated by fma against
 // a[c][c] - sum round(L[c][k]^2)); tests hold them to 1e-9 + 1e-13 |logL| of each other.
 #define GSN_ONCHIP_DIAG_TILE false
+#ifndef GSN_ONCHIP_PIVOT_RANK2
+#define GSN_ONCHIP_PIVOT_RANK2 0     // 1: two pivots per DMMA (chol8_inv_warp_r2: 10 instead of 18 DMMAs per pivot tile, 14 more shuffles per pair).
+                                     // Correct (same tests green) but 3-5 % slower: N = 64 68.6 against 70.8 M evals/s, N = 32 194 against 204 M, N = 141 11.21
+                                     // against 11.28 M -- at 18 DMMAs per tile the shapes are no longer bound by the FP64 pipe alone
+#endif
 #endif
 #ifndef GSN_ONCHIP_LAG
 #define GSN_ONCHIP_LAG 2
@@ -308,7 +313,11 @@ struct OnchipTeam {
     int expo = 0, failrow = -1;
     double2 nW;
     GSN_TRACE(5, j);
+#if GSN_ONCHIP_PIVOT_RANK2
+    chol8_inv_warp_r2(make_double2(-D.x, -D.y), lane, nW, mant, expo, failrow);
+#else
     chol8_inv_warp<GSN_ONCHIP_DIAG_TILE>(make_double2(-D.x, -D.y), lane, nW, mant, expo, failrow);
+#endif
     *tile(ta, i) = nW;
     if (T > 1) {
       __syncwarp();
@@ -394,7 +403,11 @@ constexpr int kRegCtasPerSm = GSN_REG_CTAS;
 static __device__ __noinline__ Chol8Out chol8_inv_onchip_call(double2 a, int lane) {
   Chol8Out o;
   o.mant = 1.0; o.expo = 0; o.failrow = -1;
+#if GSN_ONCHIP_PIVOT_RANK2
+  chol8_inv_warp_r2(a, lane, o.nW, o.mant, o.expo, o.failrow);
+#else
   chol8_inv_warp<GSN_ONCHIP_DIAG_TILE>(a, lane, o.nW, o.mant, o.expo, o.failrow);
+#endif
   return o;
 }
 template <int KIND>
@@ -451,6 +464,8 @@ __device__ __forceinline__ void reg_factor(const OnchipTeam<KIND>& tm) {
         const Chol8Out o = chol8_inv_onchip_call(make_double2(-D.x, -D.y), lane);
         nW = o.nW; mant = o.mant; expo = o.expo; failrow = o.failrow;
       }
+#elif GSN_ONCHIP_PIVOT_RANK2
+      chol8_inv_warp_r2(make_double2(-D.x, -D.y), lane, nW, mant, expo, failrow);
 #else
       chol8_inv_warp<GSN_ONCHIP_DIAG_TILE>(make_double2(-D.x, -D.y), lane, nW, mant, expo, failrow);
 #endif
