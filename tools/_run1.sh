@@ -1,3 +1,4 @@
-python -m pytest tests/test_gpu_onchip.py -x -q 2>&1 | tail -4
-python tools/sweep.py 16 32 48 64 96 128 141 192 > gpurun_out/sw_r2.jsonl 2>&1
-python tools/sweep_configs.py "C4 SLSN" C2 "C4 dynesty" >> gpurun_out/sw_r2.jsonl 2>&1
+timeout 600 python -m pytest tests/test_gpu_onchip.py -x -q 2>&1 | tail -4
+timeout 300 python tools/sweep.py 80 96 112 128 141 160 176 192 > gpurun_out/sw_snake.jsonl 2>&1
+timeout 300 python tools/sweep_configs.py C2 "C3 real" "C4 synthetic" >> gpurun_out/sw_snake.jsonl 2>&1
+timeout 300 python tools/latency_probe.py > gpurun_out/lat_snake.jsonl 2>&1
