@@ -352,7 +352,11 @@ struct OnchipTeam {
       // Rows are dealt out cyclically.  (The work of a row grows like i^2, so the warp that gets the last row carries 1.3 x the
       // mean at 18 rows on 5 warps; dealing the rows out from the bottom in a snake brings that to 1.07 x -- measured: N = 141
       // 11.37 against 11.28 M evals/s, three bands of 132 rows 3.55 against 4.16 M, and 9.4 M at N = 141 when a warp then takes its
-      // rows nearest to the diagonal first: the warps' relative timing matters more than their total load.)
+      // rows nearest to the diagonal first: the warps' relative timing matters more than their total load.  Likewise letting the
+      // owner of the NEXT pivot row run it early -- its tile of this column first, then pivot_row(j + 1), then its other rows; the
+      // per-column trace shows the chain standing still for 4-6 k cycles where that owner is late -- costs 20 % (N = 141 9.0 M):
+      // the warp then idles in the pivot row's waits instead of working on its panels, and with four thetas per SM it is the
+      // busy time, not one theta's critical path, that counts.)
       int i = (j + 1) + (warp - (j + 1) % T + T) % T;   // this warp's first row below j
       bool ok = true, write_ok = false;
       if (i == j + 1 && i < nt) {
