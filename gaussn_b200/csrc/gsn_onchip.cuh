@@ -347,8 +347,11 @@ struct OnchipTeam {
   }
 
   __device__ __forceinline__ void factor(int warp) const {
+    int first = warp;          // this warp's first row >= j + 1, kept incrementally (as (j + 1) + (warp - (j + 1) % T + T) % T the
+                               // two divisions by a run-time T were 9 % of all instructions executed at N = 141)
     for (int j = -1; j < nt - 1; ++j) {
       if (ld_volatile_shared(&ctl->fail) != 0) break;
+      if (first < j + 1) first += T;
       // Rows are dealt out cyclically.  (The work of a row grows like i^2, so the warp that gets the last row carries 1.3 x the
       // mean at 18 rows on 5 warps; dealing the rows out from the bottom in a snake brings that to 1.07 x -- measured: N = 141
       // 11.37 against 11.28 M evals/s, three bands of 132 rows 3.55 against 4.16 M, and 9.4 M at N = 141 when a warp then takes its
@@ -357,7 +360,7 @@ struct OnchipTeam {
       // per-column trace shows the chain standing still for 4-6 k cycles where that owner is late -- costs 20 % (N = 141 9.0 M):
       // the warp then idles in the pivot row's waits instead of working on its panels, and with four thetas per SM it is the
       // busy time, not one theta's critical path, that counts.)
-      int i = (j + 1) + (warp - (j + 1) % T + T) % T;   // this warp's first row below j
+      int i = first;
       bool ok = true, write_ok = false;
       if (i == j + 1 && i < nt) {
         ok = pivot_row(j, write_ok);
