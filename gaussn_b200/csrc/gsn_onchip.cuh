@@ -175,13 +175,14 @@ struct OnchipTeam {
   }
 
   // -K(i, j) for one tile: shifted epochs, magnifications, noise diagonal (gausSN.py:146-147), identity on padding rows.
+  template <bool kBranch = false>
   __device__ __forceinline__ double2 build(int i, int j, const Cols& q) const {
     const int row = 8 * i + (lane >> 2), col = 8 * j + (lane & 3) * 2;
     const double xr = xs[row], nbr = -bs[row];
     const double ar = kernel_has_aux<KIND>() ? aux[row] : 0.0;
     double2 v;
-    v.x = (nbr * q.ba.x) * cov_unit_sym<KIND>(kc, xr, q.x.x, ar, q.a.x, exptab);
-    v.y = (nbr * q.ba.y) * cov_unit_sym<KIND>(kc, xr, q.x.y, ar, q.a.y, exptab);
+    v.x = (nbr * q.ba.x) * cov_unit_sym<KIND, kBranch>(kc, xr, q.x.x, ar, q.a.x, exptab);
+    v.y = (nbr * q.ba.y) * cov_unit_sym<KIND, kBranch>(kc, xr, q.x.y, ar, q.a.y, exptab);
     if (i == j) {
       if (row == col) v.x -= e2[row];
       if (row == col + 1) v.y -= e2[row];
@@ -423,14 +424,14 @@ static __device__ __noinline__ Chol8Out chol8_inv_onchip_call(double2 a, int lan
 }
 template <int KIND>
 static __device__ __noinline__ double2 onchip_build_call(const OnchipTeam<KIND>* tm, int i, int j) {
-  return tm->build(i, j, tm->load_cols(j));
+  return tm->template build<true>(i, j, tm->load_cols(j));
 }
 template <int KIND>
 __device__ __forceinline__ double2 reg_build(const OnchipTeam<KIND>& tm, int i, int j, const typename OnchipTeam<KIND>::Cols& q) {
 #if GSN_REG_CALL_BUILD
   return onchip_build_call<KIND>(&tm, i, j);
 #else
-  return tm.build(i, j, q);
+  return tm.template build<true>(i, j, q);
 #endif
 }
 
@@ -544,7 +545,10 @@ __device__ __forceinline__ void reg_factor_any(const OnchipTeam<KIND>& tm, int n
 }
 
 template <int KIND, bool kReg>
-__global__ void __launch_bounds__(kReg ? 32 : kOnchipMaxWarps * 32, kReg ? kRegCtasPerSm : 1)
+#ifndef GSN_ONCHIP_BOUND_THREADS
+#define GSN_ONCHIP_BOUND_THREADS 640   // more than the 512 threads ever launched: caps the shared-memory shape at 96 registers (21 warps per SM)
+#endif
+__global__ void __launch_bounds__(kReg ? 32 : GSN_ONCHIP_BOUND_THREADS, kReg ? kRegCtasPerSm : 1)
 logl_onchip_kernel(ProblemDev pd, OnchipDev od, const double* __restrict__ theta, long long B, long long ld,
                    const double* __restrict__ hostmean, GatherOut out, int* __restrict__ info, unsigned flags,
                    unsigned* counter) {
