@@ -602,6 +602,8 @@ int gsn_problem_create(gsn_problem** out, int device, int64_t N, const double* x
       groups += (nt + 3) / 4;
       b0 = b1;
     }
+    // Dispatched while two thetas fit the shared memory of an SM: band blocks of up to 208 rows (kOnchipDispatchRows).  With one
+    // theta per SM the workspace kernels are faster (N = 216: 2.7 M evals/s here, 4.0 M there; N = 208: 4.45 against 4.09 M).
     int max_rows = gsn::kOnchipDispatchRows;
     if (const char* e = getenv("GSN_ONCHIP_MAX_ROWS")) max_rows = atoi(e);   // tuning hook; 0 switches the shape off
     const char* shape_env = getenv("GSN_FORCE_SHAPE");                       // any forced legacy shape switches it off as well

@@ -64,7 +64,7 @@ constexpr int kOnchipLag = GSN_ONCHIP_LAG;   // tiles written in column j take t
 // at N = 32.  The host builds both tables; the kernel picks by team size.
 constexpr int kOnchipLagOneWarp = 1;
 constexpr int kOnchipMaxTiles = 28;    // largest band block: 224 rows (225 live tiles = 113 KB; slot numbers fit a byte)
-constexpr int kOnchipDispatchRows = 192;   // band blocks above this run the workspace kernels (N = 224: 2.8 M evals/s here, 3.6 M there)
+constexpr int kOnchipDispatchRows = 208;   // band blocks above this (one theta per SM) run the workspace kernels: see gsn_api.cu
 constexpr int kOnchipMaxWarps = 16;
 constexpr int kOnchipMaxBlocks = 256;
 

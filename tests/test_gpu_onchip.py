@@ -31,7 +31,7 @@ def _legacy(monkeypatch, ds, kernel, mean, lens, n_images, theta, **kw):
 
 @pytest.mark.parametrize("N", [1, 2, 3, 7, 8, 9, 15, 16, 17, 31, 32, 33, 40, 63, 64, 65, 96, 100, 141, 160, 161, 192, 194, 217, 224])
 def test_every_order_up_to_224_matches_oracle_and_workspace_kernels(libgsn, monkeypatch, N):
-    """The shape is compiled for band blocks of up to 224 rows and dispatched up to 192 (GSN_ONCHIP_MAX_ROWS moves the limit)."""
+    """The shape is compiled for band blocks of up to 224 rows and dispatched up to 208, while two thetas fit an SM (GSN_ONCHIP_MAX_ROWS moves the limit)."""
     from gaussn_b200 import _engine
     monkeypatch.setenv("GSN_ONCHIP_MAX_ROWS", "224")
     rng = np.random.default_rng(5000 + N)
@@ -46,7 +46,7 @@ def test_every_order_up_to_224_matches_oracle_and_workspace_kernels(libgsn, monk
     _agree(got, _legacy(monkeypatch, ds, "ExpSquaredKernel", "UniformMean", "ConstantMagnification", n_images, theta))
 
 
-@pytest.mark.parametrize("N,n_bands,onchip", [(192, 1, 1), (193, 1, 0), (225, 1, 0), (768, 4, 1), (780, 4, 0)])
+@pytest.mark.parametrize("N,n_bands,onchip", [(192, 1, 1), (208, 1, 1), (209, 1, 0), (225, 1, 0), (832, 4, 1), (844, 4, 0)])
 def test_dispatch_limit_is_the_largest_band_block(libgsn, N, n_bands, onchip):
     from gaussn_b200 import _engine
     rng = np.random.default_rng(N)

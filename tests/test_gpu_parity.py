@@ -390,7 +390,7 @@ def test_hypothesis_random_layouts_and_theta(libgsn):
                                                        ("GibbsKernel", 2, 2, 200), ("JJKernel", 1, 2, 96), ("Matern52Kernel", 3, 2, 336),
                                                        ("ExpSquaredKernel", 4, 2, 512), ("Matern32Kernel", 3, 4, 396), ("OUKernel", 6, 2, 900)])
 def test_one_warp_per_theta_shape_on_large_batches(libgsn, monkeypatch, kernel, n_bands, n_images, N):
-    """Workspace kernels (band blocks above 192 rows; here forced for the smaller ones as well): batches of 512+ theta with
+    """Workspace kernels (band blocks above 208 rows; here forced for the smaller ones as well): batches of 512+ theta with
     band blocks of at most 336 rows run the narrow launch shape (one warp per theta); smaller batches of the same problem run
     the four-warp shape.  Both must agree with the oracle and with each other bit for bit."""
     from gaussn_b200 import _engine
@@ -455,7 +455,7 @@ def test_host_supplied_mean_with_fixed_groups(libgsn):
     assert_logl_close(got, [oracle(list(t[:2]), list(t[2:7]), l0) for t in theta], "host mean, lensing fixed")
 
 
-@pytest.mark.parametrize("kernel,n_bands,n_images,N,force", [("Matern32Kernel", 1, 2, 512, None), ("ExpSquaredKernel", 2, 2, 400, None),
+@pytest.mark.parametrize("kernel,n_bands,n_images,N,force", [("Matern32Kernel", 1, 2, 512, None), ("ExpSquaredKernel", 2, 2, 440, None),
                                                              ("OUKernel", 1, 4, 1100, None), ("PeriodicKernel", 1, 2, 420, None),
                                                              ("Matern32Kernel", 1, 2, 330, None),
                                                              ("Matern52Kernel", 3, 2, 130, "cluster4"), ("ExpSquaredKernel", 1, 2, 70, "cluster8"),
