@@ -391,7 +391,7 @@ def test_hypothesis_random_layouts_and_theta(libgsn):
                                                        ("ExpSquaredKernel", 4, 2, 512), ("Matern32Kernel", 3, 4, 396), ("OUKernel", 6, 2, 900)])
 def test_one_warp_per_theta_shape_on_large_batches(libgsn, monkeypatch, kernel, n_bands, n_images, N):
     """Workspace kernels (band blocks above 208 rows; here forced for the smaller ones as well): batches of 512+ theta with
-    band blocks of at most 336 rows run the narrow launch shape (one warp per theta); smaller batches of the same problem run
+    band blocks of at most 208 rows run the narrow launch shape (one warp per theta) once the on-chip shape is switched off; smaller batches of the same problem run
     the four-warp shape.  Both must agree with the oracle and with each other bit for bit."""
     from gaussn_b200 import _engine
     monkeypatch.setenv("GSN_FORCE_SHAPE", "legacy")
