@@ -121,16 +121,18 @@ import benchdata
 from gaussn_b200 import gausSN, kernels, meanfuncs, lensingmodels
 rank = int(os.environ["RANK"]); torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
-ds = benchdata.make_dataset(256, 1, 2); theta = benchdata.make_theta(1001, 2)
-gp = gausSN.GP(kernels.ExpSquaredKernel([0.3, 25.0]), meanfuncs.UniformMean([0.0]), lensingmodels.ConstantMagnification([20.0, 0.5]), device=rank)
-gp.x, gp.y, gp.yerr = ds["x"], ds["y"], ds["yerr"]; gp._prepare_indices(ds["x"], ds["band"], ds["image"])
-th_d = torch.as_tensor(theta, device="cuda")
-full = gp.loglikelihood_batch_sharded(th_d).cpu().numpy()
-single = gp.loglikelihood_batch(theta)
-assert np.array_equal(full, single), np.abs(full - single).max()
-for _ in range(3):   # NVLink-native path: the kernel stores into every rank's gathered buffer, then a barrier
-    fused = gp.loglikelihood_batch_sharded(th_d, fused=True).cpu().numpy()
-    assert np.array_equal(fused, single), np.abs(fused - single).max()
+# the workspace kernels (N = 256), the on-chip teams (N = 141), the register shape (N = 64, and four band blocks at N = 194)
+for N, n_bands, B in ((256, 1, 1001), (141, 1, 1001), (64, 1, 2003), (194, 4, 2003)):
+    ds = benchdata.make_dataset(N, n_bands, 2); theta = benchdata.make_theta(B, 2)
+    gp = gausSN.GP(kernels.ExpSquaredKernel([0.3, 25.0]), meanfuncs.UniformMean([0.0]), lensingmodels.ConstantMagnification([20.0, 0.5]), device=rank)
+    gp.x, gp.y, gp.yerr = ds["x"], ds["y"], ds["yerr"]; gp._prepare_indices(ds["x"], ds["band"], ds["image"])
+    th_d = torch.as_tensor(theta, device="cuda")
+    full = gp.loglikelihood_batch_sharded(th_d).cpu().numpy()
+    single = gp.loglikelihood_batch(theta)
+    assert np.array_equal(full, single, equal_nan=True), (N, np.nanmax(np.abs(full - single)))
+    for _ in range(3):   # NVLink-native path: the kernel stores into every rank's gathered buffer, then a barrier
+        fused = gp.loglikelihood_batch_sharded(th_d, fused=True).cpu().numpy()
+        assert np.array_equal(fused, single, equal_nan=True), (N, np.nanmax(np.abs(fused - single)))
 dist.destroy_process_group(); print("rank", rank, "ok")
 ''')
     env = dict(os.environ, GSN_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
